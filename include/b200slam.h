@@ -1,0 +1,213 @@
+/* b200slam -- C ABI of the Blackwell-native scan matcher and SE(2) pose-graph solver.
+ *
+ * This is the drop-in boundary for the ONE hot path of SteveMacenski/slam_toolbox:
+ *   (1) karto::ScanMatcher::MatchScan            (lib/karto_sdk/src/Mapper.cpp:534-639)
+ *   (2) the karto::ScanSolver plugin surface     (lib/karto_sdk/include/karto_sdk/Mapper.h:954-1065,
+ *       implemented today by solver_plugins::CeresSolver, solvers/ceres_solver.cpp)
+ *
+ * Plain C: opaque handles, POD structs, HOST pointers in and out, int status codes, no
+ * exceptions, no ROS / Eigen / Boost / torch types.  One handle is used by one thread at a
+ * time (the reference classes are not re-entrant either: Mapper.h:1496-1503, and every
+ * CeresSolver method takes nodes_mutex_).  There is no CPU fallback: every entry point that
+ * computes returns B200_ERR_CUDA when no sm_100 device is usable.
+ *
+ * INTEGRATION.md shows the reference-side bindings (the link-time replacement of
+ * ScanMatcher::{Create,MatchScan} and the `class B200Solver : public karto::ScanSolver`
+ * plugin adapter) that sit on top of this header.
+ */
+#ifndef B200SLAM_H
+#define B200SLAM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID_ARG 1   /* NULL handle / bad sizes / parameters ScanMatcher::Create rejects (Mapper.cpp:481-493) */
+#define B200_ERR_CUDA 2          /* no usable device or a CUDA call failed; b200_last_error() has the text */
+#define B200_ERR_UNSUPPORTED 3   /* geometry the device path cannot represent (reported, never silently approximated) */
+#define B200_ERR_NOT_FOUND 4     /* unknown node / edge id */
+#define B200_ERR_NUMERIC 5       /* singular covariance, solver produced no usable solution */
+
+const char * b200_last_error(void);
+/* Device selection for handles created afterwards by this thread (cudaSetDevice). */
+int b200_set_device(int ordinal);
+int b200_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Scan matcher
+ * ---------------------------------------------------------------------------------------- */
+
+/* Everything ScanMatcher::Create (Mapper.cpp:477) takes plus the eight karto::Mapper
+ * parameters MatchScan/operator() read at call time (Mapper.cpp:590-594, 626-627, 675-682).
+ * The *_variance_penalty fields hold the values as karto STORES them, i.e. already squared
+ * by Mapper::setParamDistanceVariancePenalty / AngleVariancePenalty (Mapper.cpp:2562-2570). */
+typedef struct b200sm_params {
+  double search_size;                 /* CorrelationSearchSpaceDimension / LoopSearchSpaceDimension (m) */
+  double resolution;                  /* ...Resolution (m)                                              */
+  double smear_deviation;             /* ...SmearDeviation (m)                                          */
+  double range_threshold;             /* LaserRangeFinder::GetRangeThreshold() (m) -> grid margin       */
+  double coarse_search_angle_offset;  /* rad */
+  double coarse_angle_resolution;     /* rad */
+  double fine_search_angle_offset;    /* rad; used as the fine angular RESOLUTION (Mapper.cpp:627)      */
+  double distance_variance_penalty;
+  double angle_variance_penalty;
+  double minimum_distance_penalty;
+  double minimum_angle_penalty;
+  int32_t use_response_expansion;
+} b200sm_params;
+
+/* What MatchScan reads from a karto::LocalizedRangeScan (Karto.h:5411-5763). */
+typedef struct b200_scan {
+  int32_t n;                 /* GetNumberOfRangeReadings()                                             */
+  const double * ranges;     /* GetRangeReadings(): n raw readings, NaN/Inf allowed (Karto.h:6869)     */
+  const double * points_xy;  /* GetPointReadings(false): n UNFILTERED world points, x,y interleaved    */
+  double sensor_pose[3];     /* GetSensorPose(): x, y, heading                                         */
+} b200_scan;
+
+/* LocalizedRangeScan::Update (Karto.h:5644-5704): the unfiltered world-frame point readings of a
+ * scan, for callers that do not already hold a karto::LocalizedRangeScan. Host libm (glibc) like
+ * the reference; out_xy = n x,y pairs. */
+int b200_point_readings(const double * ranges, int32_t n, const double sensor_pose[3],
+                        double minimum_angle, double angular_resolution, double * out_xy);
+
+typedef struct b200sm b200sm;
+
+/* ScanMatcher::Create. B200_ERR_INVALID_ARG where the reference returns NULL or throws
+ * (smear deviation outside [0.5, 10] * resolution, Mapper.h:1226-1235). */
+int b200sm_create(const b200sm_params * params, b200sm ** out);
+void b200sm_destroy(b200sm * h);
+/* Run this handle's kernels on an existing cudaStream_t (e.g. the caller's current stream). */
+int b200sm_set_stream(b200sm * h, void * cuda_stream);
+
+/* ScanMatcher::MatchScan(pScan, rBaseScans, rMean, rCovariance, doPenalize, doRefineMatch)
+ * (Mapper.cpp:534-639).  base[0..nbase) in the order of the reference's scan vector / map
+ * (order is part of the contract: SURVEY.md 7, hard part 2).  cov is row-major 3x3. */
+int b200sm_match(b200sm * h, const b200_scan * query, const b200_scan * base, int32_t nbase,
+                 int32_t do_penalize, int32_t do_refine, double mean[3], double cov[9],
+                 double * response);
+
+/* ScanMatcher::CorrelateScan (Mapper.cpp:712-862) against the grid rasterised by the last
+ * b200sm_match / b200sm_raster call. cov is in/out like the reference's rCovariance.
+ * If sums != NULL it receives the integer correlation volume, index (y*nX + x)*nAngles + a,
+ * and dims = {nX, nY, nAngles}. */
+int b200sm_raster(b200sm * h, const b200_scan * query, const b200_scan * base, int32_t nbase);
+int b200sm_correlate(b200sm * h, const b200_scan * query, const double center[3],
+                     const double search_offset[2], const double search_resolution[2],
+                     double angle_offset, double angle_resolution, int32_t do_penalize,
+                     int32_t fine, double mean[3], double cov[9], double * response,
+                     int32_t * sums, int32_t sums_cap, int32_t dims[3]);
+
+/* ScanMatcher::GetCorrelationGrid() (Mapper.h:1435): geometry + bytes of the last raster.
+ * info = width, height, stride, roi_x, roi_y, roi_w, roi_h, data_size, kernel_size. */
+int b200sm_grid_info(b200sm * h, int32_t info[9], double offset[2]);
+int b200sm_grid_copy(b200sm * h, uint8_t * out, int32_t cap);
+
+/* Batched MatchScan: the loop-closure candidate sweep (Mapper.cpp:1500-1561 calls MatchScan
+ * once per candidate chain; here all (query, chain) pairs go to the device together).
+ *   scans[0..nscans)            all candidate scans
+ *   chain_start[0..nchains]     chain j = scans[chain_start[j] .. chain_start[j+1])
+ *   pair_query/pair_chain[np]   pairs to match; both NULL = all nq*nchains pairs, query-major
+ * Outputs per pair p: response[p], mean[3p..], cov[9p..]  -- identical to calling
+ * b200sm_match(h, &queries[pair_query[p]], chain pair_chain[p], ...) one by one. */
+int b200sm_match_batch(b200sm * h, const b200_scan * queries, int32_t nq, const b200_scan * scans,
+                       int32_t nscans, const int32_t * chain_start, int32_t nchains,
+                       const int32_t * pair_query, const int32_t * pair_chain, int32_t npairs,
+                       int32_t do_penalize, int32_t do_refine, double * response, double * mean,
+                       double * cov);
+
+/* The same sweep split so that the device part can be timed with inputs resident in HBM:
+ *   upload  : host prep (lookup tables) + H2D of queries / candidate scans / pair list
+ *   run     : kernels only (asynchronous on the handle's stream); may be repeated
+ *   fetch   : D2H of the per-pair results + the libm part of the epilogue
+ * kernel_ms: device time of the dominant (correlation) kernel of the last run, from CUDA
+ * events recorded on the handle's stream around that launch (blocks until it finished). */
+int b200sm_batch_upload(b200sm * h, const b200_scan * queries, int32_t nq, const b200_scan * scans,
+                        int32_t nscans, const int32_t * chain_start, int32_t nchains,
+                        const int32_t * pair_query, const int32_t * pair_chain, int32_t npairs,
+                        int32_t do_penalize);
+int b200sm_batch_run(b200sm * h);
+int b200sm_batch_fetch(b200sm * h, double * response, double * mean, double * cov);
+int b200sm_batch_kernel_ms(b200sm * h, float * ms);
+/* per-pair best integer correlation sum and the flat index (y*nX+x)*nA+a of its first
+ * arg-max pose from the last run (parity: "integer correlation-grid indices bit-exact") */
+int b200sm_batch_best(b200sm * h, int32_t * best_sum, int32_t * best_index, int32_t * tie_count);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t b200sm_launch_count(const b200sm * h);
+
+/* ------------------------------------------------------------------------------------------
+ * SE(2) pose-graph solver  (karto::ScanSolver, Mapper.h:954-1065)
+ * ---------------------------------------------------------------------------------------- */
+
+/* The knobs CeresSolver::Configure sets (solvers/ceres_solver.cpp:96-186); defaults from
+ * b200pg_default_opts() reproduce them. */
+typedef struct b200pg_opts {
+  int32_t max_num_iterations;        /* Ceres default 50                                        */
+  double function_tolerance;         /* 1e-3  (ceres_solver.cpp:158)                            */
+  double gradient_tolerance;         /* 1e-6  (:159)                                            */
+  double parameter_tolerance;        /* 1e-3  (:160)                                            */
+  double min_relative_decrease;      /* 1e-3  (:171)                                            */
+  double initial_trust_region_radius;/* 1e4   (:173)                                            */
+  double max_trust_region_radius;    /* 1e8   (:174)                                            */
+  double min_trust_region_radius;    /* 1e-16 (:175)                                            */
+  double min_lm_diagonal;            /* 1e-6  (:177)                                            */
+  double max_lm_diagonal;            /* 1e32  (:178)                                            */
+  int32_t jacobi_scaling;            /* 1     (:169)                                            */
+  int32_t use_nonmonotonic_steps;    /* 1     (:164)                                            */
+  int32_t max_consecutive_nonmonotonic_steps; /* 3 (:165)                                       */
+  int32_t max_num_consecutive_invalid_steps;  /* 3 (:163)                                       */
+  /* linear solver (replaces SPARSE_NORMAL_CHOLESKY, :100-102): block-Jacobi PCG on the
+   * normal equations, iterated to ||r|| <= pcg_tolerance * ||b|| */
+  double pcg_tolerance;              /* 1e-10 */
+  int32_t pcg_max_iterations;        /* 20000 */
+} b200pg_opts;
+
+typedef struct b200pg_summary {
+  int32_t iterations;          /* LM iterations (successful + unsuccessful)            */
+  int32_t successful_steps;
+  int32_t pcg_iterations;      /* total over all LM iterations                         */
+  int32_t termination;         /* 0 convergence(function) 1 gradient 2 parameter 3 max-iter 4 min-radius 5 failure */
+  int32_t usable;              /* ceres::Solver::Summary::IsSolutionUsable()           */
+  double initial_cost, final_cost;
+  float solve_ms;              /* device time of the whole solve (CUDA events)         */
+  int64_t kernel_launches;
+} b200pg_summary;
+
+typedef struct b200pg b200pg;
+
+void b200pg_default_opts(b200pg_opts * o);
+int b200pg_create(const b200pg_opts * opts_or_null, b200pg ** out);
+void b200pg_destroy(b200pg * h);
+int b200pg_set_stream(b200pg * h, void * cuda_stream);
+/* ScanSolver::Reset (Mapper.h:1028; ceres_solver.cpp:272-314): drop everything, un-fix the anchor */
+int b200pg_reset(b200pg * h);
+/* ScanSolver::Clear (Mapper.h:1021): drop the corrections of the last solve only */
+int b200pg_clear(b200pg * h);
+/* ScanSolver::AddNode (ceres_solver.cpp:317-336): id = scan UniqueId, pose = corrected pose.
+ * The first node ever added becomes the gauge anchor (:333-335). */
+int b200pg_add_node(b200pg * h, int32_t id, const double pose[3]);
+/* ScanSolver::AddConstraint (ceres_solver.cpp:339-392): z = LinkInfo::GetPoseDifference(),
+ * cov = LinkInfo::GetCovariance() (row-major). The library forms the sqrt-information
+ * U = chol(cov^-1).matrixU() like :364-376. Unknown or identical nodes are refused silently
+ * in the reference (returns B200_ERR_NOT_FOUND here, state unchanged). */
+int b200pg_add_edge(b200pg * h, int32_t id_a, int32_t id_b, const double z[3], const double cov[9]);
+int b200pg_remove_node(b200pg * h, int32_t id);                 /* ceres_solver.cpp:395-425 */
+int b200pg_remove_edge(b200pg * h, int32_t id_a, int32_t id_b); /* :428-448, either orientation */
+/* ScanSolver::ModifyNode (:451-461): sets x,y and ADDS the stored yaw to pose[2]. */
+int b200pg_modify_node(b200pg * h, int32_t id, const double pose[3]);
+int b200pg_get_node(const b200pg * h, int32_t id, double pose[3]);  /* getGraph / GetNodeOrientation */
+int32_t b200pg_num_nodes(const b200pg * h);
+int32_t b200pg_num_edges(const b200pg * h);
+/* ScanSolver::Compute (:214-269): solves in place. On an unusable solution the node store
+ * and corrections are left untouched and B200_ERR_NUMERIC is returned. */
+int b200pg_solve(b200pg * h, b200pg_summary * summary_or_null);
+/* ScanSolver::GetCorrections (Mapper.h:988): all nodes after the last solve; returns count
+ * written (<= cap). Empty after b200pg_clear(). */
+int32_t b200pg_get_corrections(const b200pg * h, int32_t * ids, double * poses, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SLAM_H */

@@ -1,0 +1,83 @@
+// Shared plumbing for the b200slam library: error reporting, CUDA call checking, small RAII
+// wrappers for device / pinned-host buffers.  No compute lives here.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/b200slam.h"
+
+namespace b200 {
+
+void set_last_error(const std::string & s);
+
+struct CudaFail {
+  int code;
+};
+
+#define B200_CUDA(expr)                                                                       \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::b200::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +      \
+                             __FILE__ + ":" + std::to_string(__LINE__) + ")");                \
+      throw ::b200::CudaFail{B200_ERR_CUDA};                                                  \
+    }                                                                                         \
+  } while (0)
+
+// Fails loudly (B200_ERR_CUDA) when there is no sm_100 device: there is no CPU fallback.
+void require_device();
+
+template <class T>
+struct DevBuf {
+  T * p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf & operator=(const DevBuf &) = delete;
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  // grow-only; contents are NOT preserved
+  void reserve(size_t n)
+  {
+    if (n <= cap) return;
+    release();
+    size_t want = n + n / 4 + 16;
+    B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(T)));
+    cap = want;
+  }
+};
+
+template <class T>
+struct PinBuf {
+  T * p = nullptr;
+  size_t cap = 0;
+  ~PinBuf() { release(); }
+  PinBuf() = default;
+  PinBuf(const PinBuf &) = delete;
+  PinBuf & operator=(const PinBuf &) = delete;
+  void release()
+  {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  void reserve(size_t n)
+  {
+    if (n <= cap) return;
+    release();
+    size_t want = n + n / 4 + 16;
+    B200_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p), want * sizeof(T)));
+    cap = want;
+  }
+};
+
+}  // namespace b200

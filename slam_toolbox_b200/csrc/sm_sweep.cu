@@ -1,0 +1,777 @@
+// b200slam scan matcher, batched loop-closure sweep (generic path).
+//
+// Reference: MapperGraph::TryCloseLoop (lib/karto_sdk/src/Mapper.cpp:1500-1561) calls
+// ScanMatcher::MatchScan once per candidate chain; here every (query, chain) pair of a sweep is
+// rasterised, correlated and reduced on the device in one fused kernel launch.
+//   k_find_valid     FindValidPoints + WorldToGrid + ROI test per (pair, scan)  (M.cpp:1073-1164)
+//   k_sweep_generic  per pair: clear + smear raster, exhaustive correlation, arg-max / ties /
+//                    positional-covariance accumulators                          (M.cpp:641-966)
+//   k_sweep_fine     3x3xnA fine volumes for do_refine                           (M.cpp:621-629)
+// Compile with -fmad=false / -ffp-contract=off (bit-exact FP64, see sm_math.cuh).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "sm_math.cuh"
+#include "sm_types.cuh"
+#include "sm_device.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------
+// batch sweep, generic path
+// ------------------------------------------------------------------------------------------
+
+// ScanMatcher::FindValidPoints (M.cpp:1113-1164) + WorldToGrid + ROI test (M.cpp:1082-1088) for
+// every (pair, scan of its chain): one thread walks one scan's points in order.
+// cells[item * max_n + k] = gx | gy << 16 of the k-th point that lands inside the ROI.
+__global__ void k_find_valid(SweepDev d)
+{
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= d.nitems) return;
+  const int pair = d.item_pair[item];
+  const int scan = d.item_scan[item];
+  const int q = d.pair_query[pair];
+  const double vx = d.qgeom[q * 4 + 0], vy = d.qgeom[q * 4 + 1];
+  const double ox = d.qgeom[q * 4 + 2], oy = d.qgeom[q * 4 + 3];
+  const double * pts = d.points + 2 * (size_t)d.scan_pt_start[scan];
+  const int n = d.scan_pt_start[scan + 1] - d.scan_pt_start[scan];
+  int32_t * out = d.cells + (size_t)item * d.max_n;
+  ValidPointState st;
+  st.init();
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    double cx = pts[2 * i], cy = pts[2 * i + 1];
+    int lo, hi;
+    st.step(i, cx, cy, vx, vy, lo, hi);
+    for (int t = lo; t < hi; ++t) {
+      int gx = world_to_grid(pts[2 * t], ox, d.scale);
+      int gy = world_to_grid(pts[2 * t + 1], oy, d.scale);
+      if (is_up_to(gx, d.roi_w) && is_up_to(gy, d.roi_h)) out[cnt++] = gx | (gy << 16);
+    }
+  }
+  d.cell_count[item] = cnt;
+}
+
+__device__ __forceinline__ double block_max(double v, double * scratch)
+{
+  for (int o = 16; o > 0; o >>= 1) {
+    double other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other > v ? other : v;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double r = scratch[0];
+  for (int i = 1; i < nw; ++i) r = scratch[i] > r ? scratch[i] : r;
+  __syncthreads();
+  return r;
+}
+
+// exclusive prefix sum of one int per thread over the block; returns the exclusive value and
+// writes the block total
+__device__ __forceinline__ int block_exclusive_scan(int v, int * scratch, int & total)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  int base = 0, tot = 0;
+  for (int i = 0; i < nw; ++i) {
+    if (i < warp) base += scratch[i];
+    tot += scratch[i];
+  }
+  __syncthreads();
+  total = tot;
+  return base + inc - v;
+}
+
+// response of pose (xy, a) from its integer sum, exactly as ScanMatcher::operator() builds it
+// (M.cpp:670-685)
+__device__ __forceinline__ double pose_response(const SweepDev & d, int q, int sum, int x, int y, int a)
+{
+  double r = (double)sum;
+  r /= d.norm;
+  if (d.do_penalize && !double_equal(r, 0.0)) {
+    double dp = distance_penalty(d.sqx[q * d.nX + x], d.sqy[q * d.nY + y], d.dist_var, d.min_dist_pen);
+    double ap = d.angpen[q * d.nA + a];
+    r *= (dp * ap);
+  }
+  return r;
+}
+
+// The on-device part of CorrelateScan's reduction (M.cpp:775-829) and of
+// ComputePositionalCovariance (M.cpp:893-933) for one pair whose integer volume is in `sums`
+// (index (y*nX+x)*nA + a).  `probs` = P doubles of scratch.  Everything that needs libm
+// (heading average) is finished on the host from the tie list.
+__device__ void pair_epilogue(const SweepDev & d, int pair, int q, const int32_t * sums,
+                              double * probs, double * s_dscratch, int * s_iscratch)
+{
+  const int P = d.nX * d.nY, nA = d.nA;
+  PairOut & out = d.out[pair];
+  // best response + per-cell max over angles (the m_pSearchSpaceProbs image, M.cpp:781-799)
+  double lbest = -1.0;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const int x = p % d.nX, y = p / d.nX;
+    double pm = 0.0;   // Grid<double>::Clear() initial value, M.cpp:727
+    for (int a = 0; a < nA; ++a) {
+      int s = sums[(size_t)p * nA + a];
+      double r = pose_response(d, q, s, x, y, a);
+      pm = r > pm ? r : pm;
+      lbest = r > lbest ? r : lbest;
+    }
+    probs[p] = pm;
+  }
+  const double best = block_max(lbest, s_dscratch);
+
+  // ordered tie list: poses with DoubleEqual(response, best) in array order (M.cpp:807-817)
+  // each thread owns a contiguous run of cells so that ranks follow array order
+  const int per = (P + blockDim.x - 1) / blockDim.x;
+  const int p0 = min(P, (int)threadIdx.x * per), p1 = min(P, p0 + per);
+  int cnt = 0;
+  for (int p = p0; p < p1; ++p) {
+    const int x = p % d.nX, y = p / d.nX;
+    for (int a = 0; a < nA; ++a)
+      if (double_equal(pose_response(d, q, sums[(size_t)p * nA + a], x, y, a), best)) ++cnt;
+  }
+  int total = 0;
+  int rank = block_exclusive_scan(cnt, s_iscratch, total);
+  for (int p = p0; p < p1 && rank < kMaxTies; ++p) {
+    const int x = p % d.nX, y = p / d.nX;
+    for (int a = 0; a < nA && rank < kMaxTies; ++a)
+      if (double_equal(pose_response(d, q, sums[(size_t)p * nA + a], x, y, a), best)) {
+        out.ties[rank++] = p * nA + a;
+      }
+  }
+  __syncthreads();
+  __shared__ double s_avg[2];
+  if (threadIdx.x == 0) {
+    out.best = best;
+    out.best_sum = total > 0 ? sums[out.ties[0]] : 0;
+    out.tie_count = total;
+    double ax = 0.0, ay = 0.0;
+    const int m = total < kMaxTies ? total : kMaxTies;
+    for (int t = 0; t < m; ++t) {   // averagePosition += pose position, in order (M.cpp:809)
+      int p = out.ties[t] / nA;
+      ax += d.newx[q * d.nX + p % d.nX];
+      ay += d.newy[q * d.nY + p / d.nX];
+    }
+    if (total > 0) { ax /= total; ay /= total; }
+    s_avg[0] = ax; s_avg[1] = ay;
+    out.avg_x = ax; out.avg_y = ay;
+  }
+  __syncthreads();
+  // positional covariance accumulators (M.cpp:893-933): cells with response >= best - 0.1,
+  // summed in (y, x) order. Terms are formed in parallel, compacted in order, then added
+  // sequentially so the additions happen in the reference's order.
+  const double dx = s_avg[0] - d.center[q * 3 + 0], dy = s_avg[1] - d.center[q * 3 + 1];
+  int c2 = 0;
+  for (int p = p0; p < p1; ++p) if (probs[p] >= (best - 0.1)) ++c2;
+  int tot2 = 0;
+  int r2 = block_exclusive_scan(c2, s_iscratch, tot2);
+  double * terms = probs + P;   // 4 * P doubles of scratch after the probs image
+  for (int p = p0; p < p1; ++p) {
+    double resp = probs[p];
+    if (resp >= (best - 0.1)) {
+      double x = d.xrel[q * d.nX + p % d.nX], y = d.yrel[q * d.nY + p / d.nX];
+      terms[4 * r2 + 0] = resp;
+      terms[4 * r2 + 1] = (square(x - dx) * resp);
+      terms[4 * r2 + 2] = ((x - dx) * (y - dy) * resp);
+      terms[4 * r2 + 3] = (square(y - dy) * resp);
+      ++r2;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double norm = 0, axx = 0, axy = 0, ayy = 0;
+    for (int t = 0; t < tot2; ++t) {
+      norm += terms[4 * t + 0];
+      axx += terms[4 * t + 1];
+      axy += terms[4 * t + 2];
+      ayy += terms[4 * t + 3];
+    }
+    out.norm = norm; out.acc_xx = axx; out.acc_xy = axy; out.acc_yy = ayy;
+  }
+  __syncthreads();
+}
+
+// Generic fused sweep kernel: one CTA walks pairs p = blockIdx.x, blockIdx.x + gridDim.x, ...
+// For each pair: clear its workspace grid (Grid::Clear, M.cpp:1034), max-stamp the smear kernel
+// of every valid point (AddScan, M.cpp:1080-1104), correlate all (x, y, theta) poses against it
+// (M.cpp:641-694 + 1172-1208) and reduce (pair_epilogue).  The grid lives in a per-CTA global
+// workspace (L2 resident) and is read through L1.
+__global__ void __launch_bounds__(kSweepThreads) k_sweep_generic(SweepDev d)
+{
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  int32_t * s_off = reinterpret_cast<int32_t *>(s_raw);   // nA * n lookup table of this pair's query
+  __shared__ double s_dscratch[32];
+  __shared__ int s_iscratch[32];
+
+  uint8_t * grid = d.ws_grid + (size_t)blockIdx.x * d.ws_grid_pitch;
+  int32_t * sums = d.ws_sums + (size_t)blockIdx.x * d.ws_sums_pitch;
+  double * probs = d.ws_probs + (size_t)blockIdx.x * d.ws_probs_pitch;
+  const int P = d.nX * d.nY, nA = d.nA, n = d.n;
+  const int half = d.ksize / 2, taps = d.ksize * d.ksize;
+  int last_q = -1;
+
+  for (int pair = blockIdx.x; pair < d.npairs; pair += gridDim.x) {
+    const int q = d.pair_query[pair];
+    // (1) clear
+    {
+      uint4 * g4 = reinterpret_cast<uint4 *>(grid);
+      const int n16 = d.data_size / 16;
+      for (int i = threadIdx.x; i < n16; i += blockDim.x) g4[i] = make_uint4(0, 0, 0, 0);
+      for (int i = n16 * 16 + threadIdx.x; i < d.data_size; i += blockDim.x) grid[i] = 0;
+    }
+    if (q != last_q) {
+      for (int i = threadIdx.x; i < nA * n; i += blockDim.x) s_off[i] = d.offsets[(size_t)q * nA * n + i];
+      last_q = q;
+    }
+    __syncthreads();
+    // (2) raster
+    const int it0 = d.pair_item_start[pair], it1 = d.pair_item_start[pair + 1];
+    if (d.order_dependent) {
+      // AddScan's "already 100" test (M.cpp:1093-1096) makes the raster depend on insertion order
+      // when the smear kernel has 100s off-centre: replay that greedy rule sequentially, stamping
+      // only the 100-valued taps, and drop the points the reference would skip.
+      if (threadIdx.x == 0) {
+        for (int it = it0; it < it1; ++it) {
+          int32_t * cl = d.cells + (size_t)it * d.max_n;
+          const int cn = d.cell_count[it];
+          for (int k = 0; k < cn; ++k) {
+            if (cl[k] < 0) continue;
+            int gx = (cl[k] & 0xFFFF) + d.roi_x, gy = (cl[k] >> 16) + d.roi_y;
+            if (grid[(size_t)gy * d.stride + gx] == kOccupied) { cl[k] = -1; continue; }
+            for (int t = 0; t < taps; ++t)
+              if (d.kern[t] == kOccupied)
+                grid[(size_t)(gy + t / d.ksize - half) * d.stride + gx + t % d.ksize - half] = kOccupied;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (int it = it0; it < it1; ++it) {
+      const int32_t * cl = d.cells + (size_t)it * d.max_n;
+      const int total = d.cell_count[it] * taps;
+      for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        int32_t cell = cl[t / taps];
+        if (cell < 0) continue;
+        const int k = t % taps;
+        uint32_t kv = d.kern[k];
+        if (kv == 0) continue;
+        int gx = (cell & 0xFFFF) + d.roi_x + (k % d.ksize) - half;
+        int gy = (cell >> 16) + d.roi_y + (k / d.ksize) - half;
+        atomic_max_u8(grid + (size_t)gy * d.stride + gx, kv);
+      }
+    }
+    __syncthreads();
+    // (3) correlate: items = (angle, pose), angle-major so a warp shares one lookup row
+    const int32_t * pos = d.posidx + (size_t)q * P;
+    for (int item = threadIdx.x; item < nA * P; item += blockDim.x) {
+      const int a = item / P, p = item - a * P;
+      const int base = pos[p];
+      const int32_t * off = s_off + a * n;
+      int acc = 0;
+#pragma unroll 8
+      for (int i = 0; i < n; ++i) {
+        int idx = base + off[i];
+        if ((unsigned)idx < (unsigned)d.data_size) acc += grid[idx];
+      }
+      sums[(size_t)p * nA + a] = acc;
+    }
+    __syncthreads();
+    // (4) reduce
+    pair_epilogue(d, pair, q, sums, probs, s_dscratch, s_iscratch);
+  }
+}
+
+// fine pass of the batch: 3x3xnA volume per pair, lookup table per pair (the search centre is
+// the pair's coarse mean). Re-rasterises the pair's grid, writes only the integer volume; the
+// (tiny) reduction incl. ComputeAngularCovariance runs on the host.
+__global__ void __launch_bounds__(kSweepThreads) k_sweep_fine(SweepDev d, FineDev f)
+{
+  uint8_t * grid = d.ws_grid + (size_t)blockIdx.x * d.ws_grid_pitch;
+  const int half = d.ksize / 2, taps = d.ksize * d.ksize;
+  for (int pair = blockIdx.x; pair < d.npairs; pair += gridDim.x) {
+    {
+      uint4 * g4 = reinterpret_cast<uint4 *>(grid);
+      const int n16 = d.data_size / 16;
+      for (int i = threadIdx.x; i < n16; i += blockDim.x) g4[i] = make_uint4(0, 0, 0, 0);
+      for (int i = n16 * 16 + threadIdx.x; i < d.data_size; i += blockDim.x) grid[i] = 0;
+    }
+    __syncthreads();
+    const int it0 = d.pair_item_start[pair], it1 = d.pair_item_start[pair + 1];
+    // cells dropped by AddScan's occupancy test were marked < 0 by the coarse pass: plain max-stamp
+    for (int it = it0; it < it1; ++it) {
+      const int32_t * cl = d.cells + (size_t)it * d.max_n;
+      const int total = d.cell_count[it] * taps;
+      for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        int32_t cell = cl[t / taps];
+        if (cell < 0) continue;
+        const int k = t % taps;
+        uint32_t kv = d.kern[k];
+        if (kv == 0) continue;
+        int gx = (cell & 0xFFFF) + d.roi_x + (k % d.ksize) - half;
+        int gy = (cell >> 16) + d.roi_y + (k / d.ksize) - half;
+        atomic_max_u8(grid + (size_t)gy * d.stride + gx, kv);
+      }
+    }
+    __syncthreads();
+    const int P = f.P, nA = f.nA, n = d.n;
+    const int32_t * off = f.offsets + (size_t)pair * nA * n;
+    const int32_t * pos = f.posidx + (size_t)pair * P;
+    int32_t * sums = f.sums + (size_t)pair * P * nA;
+    // one warp per (pose, angle): lanes split the beams
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int item = warp; item < P * nA; item += nw) {
+      const int p = item / nA, a = item - p * nA;
+      const int base = pos[p];
+      int acc = 0;
+      for (int i = lane; i < n; i += 32) {
+        int idx = base + off[a * n + i];
+        if ((unsigned)idx < (unsigned)d.data_size) acc += grid[idx];
+      }
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) sums[item] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+
+void SweepHost::release()
+{
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  ev0 = ev1 = nullptr;
+  uploaded = ran = false;
+}
+
+template <class T>
+static void h2d(DevBuf<T> & dst, const T * src, size_t count, cudaStream_t s)
+{
+  dst.reserve(count);
+  if (count) B200_CUDA(cudaMemcpyAsync(dst.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+
+static GridGeom geom_for_query(const b200sm * h, const b200_scan * q)
+{
+  GridGeom g;
+  g.width = h->g.width; g.height = h->g.height; g.stride = h->g.stride;
+  g.roi_x = h->g.roi_x; g.roi_y = h->g.roi_y; g.roi_w = h->g.roi_w; g.roi_h = h->g.roi_h;
+  g.data_size = h->g.data_size; g.ksize = h->g.ksize; g.order_dependent = h->g.order_dependent;
+  g.scale = h->g.scale;
+  set_grid_offset(g, q);
+  return g;
+}
+
+static void coarse_search(const b200sm * h, double off[2], double res[2])
+{
+  double r = 1.0 / h->g.scale;
+  double dim = (double)h->probs_side;
+  off[0] = off[1] = 0.5 * (dim - 1) * r;   // M.cpp:579-581
+  res[0] = res[1] = 2 * r;                 // M.cpp:584-585
+}
+
+static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b200_scan * scans, int nscans,
+                        const int32_t * chain_start, int nchains, const int32_t * pair_query,
+                        const int32_t * pair_chain, int npairs, bool do_penalize)
+{
+  SweepHost & S = h->sweep;
+  S.uploaded = S.ran = false;
+  if (!queries || nq <= 0 || !scans || nscans <= 0 || !chain_start || nchains <= 0) {
+    set_last_error("sweep: empty or NULL input");
+    return B200_ERR_INVALID_ARG;
+  }
+  if ((pair_query == nullptr) != (pair_chain == nullptr)) { set_last_error("sweep: give both pair arrays or neither"); return B200_ERR_INVALID_ARG; }
+  if (!pair_query) npairs = nq * nchains;
+  if (npairs <= 0) { set_last_error("sweep: no pairs"); return B200_ERR_INVALID_ARG; }
+  const int n = queries[0].n;
+  for (int q = 0; q < nq; ++q) {
+    if (queries[q].n != n || n <= 0 || !queries[q].ranges || !queries[q].points_xy) {
+      set_last_error("sweep: every query needs the same, non-zero number of readings");
+      return B200_ERR_INVALID_ARG;
+    }
+  }
+  if (chain_start[0] != 0 || chain_start[nchains] != nscans) { set_last_error("sweep: chain_start must cover scans[0..nscans)"); return B200_ERR_INVALID_ARG; }
+  for (int c = 0; c < nchains; ++c)
+    if (chain_start[c + 1] < chain_start[c]) { set_last_error("sweep: chain_start must be non-decreasing"); return B200_ERR_INVALID_ARG; }
+  h->ensure_stream();
+  cudaStream_t st = h->stream;
+  const GridGeom & g0 = h->g;
+
+  // ---- coarse plans, one per query ----
+  double off[2], res[2];
+  coarse_search(h, off, res);
+  S.plans.assign(nq, CorrPlan());
+  for (int q = 0; q < nq; ++q) {
+    GridGeom g = geom_for_query(h, &queries[q]);
+    int rc = build_plan(g, h->probs_side, h->p, &queries[q], queries[q].sensor_pose, off, res,
+                        h->p.coarse_search_angle_offset, h->p.coarse_angle_resolution, false, S.plans[q]);
+    if (rc != B200_OK) return rc;
+  }
+  const CorrPlan & p0 = S.plans[0];
+  const int nX = p0.nX, nY = p0.nY, nA = p0.nA, P = nX * nY;
+  if ((size_t)nA * n * sizeof(int32_t) > 200 * 1024) {
+    set_last_error("sweep: lookup table does not fit shared memory (angle window too wide for the batched path)");
+    return B200_ERR_UNSUPPORTED;
+  }
+  S.nq = nq; S.n = n; S.npairs = npairs; S.nscans = nscans; S.do_penalize = do_penalize;
+  S.queries.assign(queries, queries + nq);
+  S.scans.assign(scans, scans + nscans);
+  S.chain_start.assign(chain_start, chain_start + nchains + 1);
+  S.pair_query.resize(npairs); S.pair_chain.resize(npairs);
+  for (int p = 0; p < npairs; ++p) {
+    int q = pair_query ? pair_query[p] : p / nchains;
+    int c = pair_chain ? pair_chain[p] : p % nchains;
+    if (q < 0 || q >= nq || c < 0 || c >= nchains) { set_last_error("sweep: pair index out of range"); return B200_ERR_INVALID_ARG; }
+    S.pair_query[p] = q; S.pair_chain[p] = c;
+  }
+
+  // ---- per-query tables ----
+  {
+    const size_t no = (size_t)nq * nA * n, np = (size_t)nq * P;
+    S.h_i.reserve(no + np);
+    for (int q = 0; q < nq; ++q) {
+      const CorrPlan & pl = S.plans[q];
+      for (size_t i = 0; i < (size_t)nA * n; ++i) S.h_i.p[(size_t)q * nA * n + i] = device_offset(pl.offsets[i], g0.data_size);
+      for (int y = 0; y < nY; ++y)
+        for (int x = 0; x < nX; ++x) S.h_i.p[no + (size_t)q * P + (size_t)y * nX + x] = pl.xs[x] + pl.ys[y] * g0.stride;
+    }
+    h2d(S.d_offsets, S.h_i.p, no, st);
+    h2d(S.d_posidx, S.h_i.p + no, np, st);
+    // doubles: qgeom[4], center[3], then 6 arrays of nX/nY, angpen
+    const size_t per = 4 + 3 + 3 * (size_t)nX + 3 * (size_t)nY + nA;
+    S.h_d.reserve(per * nq);
+    double * qgeom = S.h_d.p, * center = qgeom + 4 * (size_t)nq, * xrel = center + 3 * (size_t)nq, * newx = xrel + (size_t)nq * nX,
+           * sqx = newx + (size_t)nq * nX, * yrel = sqx + (size_t)nq * nX, * newy = yrel + (size_t)nq * nY,
+           * sqy = newy + (size_t)nq * nY, * angpen = sqy + (size_t)nq * nY;
+    for (int q = 0; q < nq; ++q) {
+      const CorrPlan & pl = S.plans[q];
+      GridGeom g = geom_for_query(h, &queries[q]);
+      qgeom[4 * q + 0] = queries[q].sensor_pose[0]; qgeom[4 * q + 1] = queries[q].sensor_pose[1];   // view point, M.cpp:574
+      qgeom[4 * q + 2] = g.off_x; qgeom[4 * q + 3] = g.off_y;
+      for (int i = 0; i < 3; ++i) center[3 * q + i] = pl.center[i];
+      for (int x = 0; x < nX; ++x) { xrel[(size_t)q * nX + x] = pl.xrel[x]; newx[(size_t)q * nX + x] = pl.newx[x]; sqx[(size_t)q * nX + x] = pl.sqx[x]; }
+      for (int y = 0; y < nY; ++y) { yrel[(size_t)q * nY + y] = pl.yrel[y]; newy[(size_t)q * nY + y] = pl.newy[y]; sqy[(size_t)q * nY + y] = pl.sqy[y]; }
+      for (int a = 0; a < nA; ++a) angpen[(size_t)q * nA + a] = pl.angpen[a];
+    }
+    h2d(S.d_qd, S.h_d.p, per * nq, st);
+  }
+  B200_CUDA(cudaStreamSynchronize(st));   // h_i / h_d are reused below
+
+  // ---- candidate scans ----
+  std::vector<int32_t> pt_start(nscans + 1, 0);
+  int max_n = 0;
+  bool contiguous = true;
+  for (int s = 0; s < nscans; ++s) {
+    if (scans[s].n < 0 || (scans[s].n > 0 && !scans[s].points_xy)) { set_last_error("sweep: candidate scan without points"); return B200_ERR_INVALID_ARG; }
+    pt_start[s + 1] = pt_start[s] + scans[s].n;
+    max_n = std::max(max_n, scans[s].n);
+    if (s > 0 && scans[s].points_xy != scans[s - 1].points_xy + 2 * (size_t)scans[s - 1].n) contiguous = false;
+  }
+  const size_t npts = (size_t)pt_start[nscans];
+  S.d_points.reserve(2 * npts + 2);
+  if (contiguous) {
+    // caller laid the scans out back to back (pinned or not): one copy straight from its buffer
+    B200_CUDA(cudaMemcpyAsync(S.d_points.p, scans[0].points_xy, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    S.h_d.reserve(2 * npts);
+    for (int s = 0; s < nscans; ++s)
+      std::memcpy(S.h_d.p + 2 * (size_t)pt_start[s], scans[s].points_xy, 2 * (size_t)scans[s].n * sizeof(double));
+    B200_CUDA(cudaMemcpyAsync(S.d_points.p, S.h_d.p, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  S.max_n = std::max(max_n, 1);
+
+  // ---- pairs and items ----
+  std::vector<int32_t> pair_item_start(npairs + 1, 0);
+  for (int p = 0; p < npairs; ++p) {
+    int c = S.pair_chain[p];
+    pair_item_start[p + 1] = pair_item_start[p] + (chain_start[c + 1] - chain_start[c]);
+  }
+  const int nitems = pair_item_start[npairs];
+  S.nitems = nitems;
+  {
+    const size_t tot = (size_t)(nscans + 1) + npairs + (npairs + 1) + 2 * (size_t)nitems;
+    S.h_i.reserve(tot);
+    int32_t * a_pt = S.h_i.p, * a_pq = a_pt + nscans + 1, * a_pis = a_pq + npairs, * a_ip = a_pis + npairs + 1, * a_is = a_ip + nitems;
+    std::memcpy(a_pt, pt_start.data(), (nscans + 1) * sizeof(int32_t));
+    std::memcpy(a_pq, S.pair_query.data(), npairs * sizeof(int32_t));
+    std::memcpy(a_pis, pair_item_start.data(), (npairs + 1) * sizeof(int32_t));
+    for (int p = 0; p < npairs; ++p) {
+      int c = S.pair_chain[p];
+      for (int k = 0; k < chain_start[c + 1] - chain_start[c]; ++k) {
+        a_ip[pair_item_start[p] + k] = p;
+        a_is[pair_item_start[p] + k] = chain_start[c] + k;
+      }
+    }
+    h2d(S.d_scan_pt_start, a_pt, nscans + 1, st);
+    h2d(S.d_pair_query, a_pq, npairs, st);
+    h2d(S.d_pair_item_start, a_pis, npairs + 1, st);
+    h2d(S.d_item_pair, a_ip, std::max(nitems, 1), st);
+    h2d(S.d_item_scan, a_is, std::max(nitems, 1), st);
+  }
+  S.d_cells.reserve((size_t)std::max(nitems, 1) * S.max_n);
+  S.d_cell_count.reserve(std::max(nitems, 1));
+  if (S.d_kernel.cap == 0) h2d(S.d_kernel, g0.kernel.data(), g0.kernel.size(), st);
+
+  // ---- workspaces: one per resident CTA ----
+  int dev = 0, sms = 148;
+  B200_CUDA(cudaGetDevice(&dev));
+  B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = (size_t)nA * n * sizeof(int32_t);
+  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  S.blocks = std::min(npairs, sms * per_sm);
+  const size_t gpitch = ((size_t)g0.data_size + 255) & ~(size_t)255;
+  const size_t spitch = ((size_t)P * nA + 63) & ~(size_t)63;
+  const size_t ppitch = ((size_t)5 * P + 31) & ~(size_t)31;
+  S.d_ws_grid.reserve(gpitch * S.blocks);
+  S.d_ws_sums.reserve(spitch * S.blocks);
+  S.d_ws_probs.reserve(ppitch * S.blocks);
+  S.d_out.reserve(npairs);
+  S.h_out.reserve(npairs);
+
+  SweepDev & d = S.dev;
+  d.stride = g0.stride; d.roi_x = g0.roi_x; d.roi_y = g0.roi_y; d.roi_w = g0.roi_w; d.roi_h = g0.roi_h;
+  d.data_size = g0.data_size; d.ksize = g0.ksize; d.order_dependent = g0.order_dependent ? 1 : 0;
+  d.scale = g0.scale; d.kern = S.d_kernel.p;
+  d.nX = nX; d.nY = nY; d.nA = nA; d.n = n;
+  d.norm = (double)((uint32_t)n * (uint32_t)kOccupied);
+  d.do_penalize = do_penalize ? 1 : 0;
+  d.dist_var = h->p.distance_variance_penalty; d.min_dist_pen = h->p.minimum_distance_penalty;
+  d.offsets = S.d_offsets.p; d.posidx = S.d_posidx.p;
+  {
+    double * base = S.d_qd.p;
+    d.qgeom = base; d.center = base + 4 * (size_t)nq;
+    d.xrel = d.center + 3 * (size_t)nq; d.newx = d.xrel + (size_t)nq * nX; d.sqx = d.newx + (size_t)nq * nX;
+    d.yrel = d.sqx + (size_t)nq * nX; d.newy = d.yrel + (size_t)nq * nY; d.sqy = d.newy + (size_t)nq * nY;
+    d.angpen = d.sqy + (size_t)nq * nY;
+  }
+  d.points = S.d_points.p; d.scan_pt_start = S.d_scan_pt_start.p;
+  d.npairs = npairs; d.nitems = nitems; d.max_n = S.max_n;
+  d.pair_query = S.d_pair_query.p; d.pair_item_start = S.d_pair_item_start.p;
+  d.item_pair = S.d_item_pair.p; d.item_scan = S.d_item_scan.p;
+  d.cells = S.d_cells.p; d.cell_count = S.d_cell_count.p;
+  d.ws_grid = S.d_ws_grid.p; d.ws_grid_pitch = gpitch;
+  d.ws_sums = S.d_ws_sums.p; d.ws_sums_pitch = spitch;
+  d.ws_probs = S.d_ws_probs.p; d.ws_probs_pitch = ppitch;
+  d.out = S.d_out.p;
+  if (!S.ev0) { B200_CUDA(cudaEventCreate(&S.ev0)); B200_CUDA(cudaEventCreate(&S.ev1)); }
+  B200_CUDA(cudaStreamSynchronize(st));
+  S.uploaded = true;
+  return B200_OK;
+}
+
+static int sweep_run(b200sm * h)
+{
+  SweepHost & S = h->sweep;
+  if (!S.uploaded) { set_last_error("sweep: nothing uploaded"); return B200_ERR_INVALID_ARG; }
+  cudaStream_t st = h->stream;
+  const SweepDev & d = S.dev;
+  if (S.nitems > 0) {
+    k_find_valid<<<(S.nitems + 63) / 64, 64, 0, st>>>(d);
+    B200_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+  const size_t smem = (size_t)d.nA * d.n * sizeof(int32_t);
+  B200_CUDA(cudaFuncSetAttribute(k_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B200_CUDA(cudaEventRecord(S.ev0, st));
+  k_sweep_generic<<<S.blocks, kSweepThreads, smem, st>>>(d);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaEventRecord(S.ev1, st));
+  h->launches++;
+  S.ran = true;
+  return B200_OK;
+}
+
+// finish one pair on the host from the device reduction: heading average (libm) + covariance tail
+static bool finish_pair(const b200sm * h, const SweepHost & S, int pair, const PairOut & o, double * response,
+                        double * mean, double * cov)
+{
+  const CorrPlan & pl = S.plans[S.pair_query[pair]];
+  if (o.tie_count <= 0 || o.tie_count > kMaxTies) return false;
+  if (h->p.use_response_expansion && double_equal(o.best, 0.0)) return false;   // M.cpp:594-619 needs more passes
+  double thetaX = 0.0, thetaY = 0.0;
+  for (int t = 0; t < o.tie_count; ++t) {   // M.cpp:811-813
+    double heading = pl.heading[o.ties[t] % pl.nA];
+    thetaX += cos(heading); thetaY += sin(heading);
+  }
+  thetaX /= o.tie_count; thetaY /= o.tie_count;
+  mean[0] = o.avg_x; mean[1] = o.avg_y; mean[2] = atan2(thetaY, thetaX);
+  for (int i = 0; i < 9; ++i) cov[i] = 0.0;
+  cov[0] = cov[4] = cov[8] = 1.0;   // SetToIdentity, M.cpp:882
+  if (o.best < kTolerance) {
+    cov[0] = kMaxVariance; cov[4] = kMaxVariance; cov[8] = 4 * square(pl.ang_res);
+  } else {
+    finish_positional_cov(o.norm, o.acc_xx, o.acc_xy, o.acc_yy, o.best, pl.sp_res, pl.ang_res, cov);
+  }
+  *response = o.best > 1.0 ? 1.0 : o.best;
+  return true;
+}
+
+static void chain_of_pair(const SweepHost & S, int pair, const b200_scan *& base, int & nbase)
+{
+  int c = S.pair_chain[pair];
+  base = S.scans.data() + S.chain_start[c];
+  nbase = S.chain_start[c + 1] - S.chain_start[c];
+}
+
+static int sweep_fetch(b200sm * h, bool do_refine, double * response, double * mean, double * cov)
+{
+  SweepHost & S = h->sweep;
+  if (!S.ran) { set_last_error("sweep: run before fetch"); return B200_ERR_INVALID_ARG; }
+  if (!response || !mean || !cov) return B200_ERR_INVALID_ARG;
+  cudaStream_t st = h->stream;
+  B200_CUDA(cudaMemcpyAsync(S.h_out.p, S.d_out.p, (size_t)S.npairs * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  std::vector<char> done(S.npairs, 0);
+  for (int p = 0; p < S.npairs; ++p) {
+    if (!finish_pair(h, S, p, S.h_out.p[p], &response[p], &mean[3 * p], &cov[9 * p])) {
+      // tie-list overflow / response expansion: this pair goes through the single-match path
+      const b200_scan * base; int nbase;
+      chain_of_pair(S, p, base, nbase);
+      response[p] = do_match(h, &S.queries[S.pair_query[p]], base, nbase, S.do_penalize, do_refine, &mean[3 * p], &cov[9 * p]);
+      done[p] = 1;
+    }
+  }
+  if (!do_refine) return B200_OK;
+
+  // ---- fine pass (M.cpp:621-629): per-pair plan centred on the coarse mean ----
+  const double r = 1.0 / h->g.scale;
+  double coff[2], cres[2];
+  coarse_search(h, coff, cres);
+  double foff[2] = {cres[0] * 0.5, cres[1] * 0.5}, fres[2] = {r, r};
+  std::vector<CorrPlan> fp(S.npairs);
+  std::vector<GridGeom> fg(S.npairs);
+  int P = 0, nA = 0;
+  for (int p = 0; p < S.npairs; ++p) {
+    const b200_scan * q = &S.queries[S.pair_query[p]];
+    fg[p] = geom_for_query(h, q);
+    double c2[3] = {mean[3 * p], mean[3 * p + 1], mean[3 * p + 2]};
+    if (done[p]) { c2[0] = q->sensor_pose[0]; c2[1] = q->sensor_pose[1]; c2[2] = q->sensor_pose[2]; }   // placeholder plan, result unused
+    int rc = build_plan(fg[p], h->probs_side, h->p, q, c2, foff, fres, 0.5 * h->p.coarse_angle_resolution,
+                        h->p.fine_search_angle_offset, true, fp[p]);
+    if (rc != B200_OK) return rc;
+    P = fp[p].nX * fp[p].nY; nA = fp[p].nA;
+  }
+  const int n = S.n;
+  const size_t no = (size_t)S.npairs * nA * n, np = (size_t)S.npairs * P, ns = (size_t)S.npairs * P * nA;
+  S.h_i.reserve(no + np + ns);
+  for (int p = 0; p < S.npairs; ++p) {
+    for (size_t i = 0; i < (size_t)nA * n; ++i) S.h_i.p[(size_t)p * nA * n + i] = device_offset(fp[p].offsets[i], h->g.data_size);
+    for (int y = 0; y < fp[p].nY; ++y)
+      for (int x = 0; x < fp[p].nX; ++x)
+        S.h_i.p[no + (size_t)p * P + (size_t)y * fp[p].nX + x] = fp[p].xs[x] + fp[p].ys[y] * h->g.stride;
+  }
+  h2d(S.d_fine_off, S.h_i.p, no, st);
+  h2d(S.d_fine_pos, S.h_i.p + no, np, st);
+  S.d_fine_sums.reserve(ns);
+  FineDev f{P, nA, S.d_fine_off.p, S.d_fine_pos.p, S.d_fine_sums.p};
+  k_sweep_fine<<<S.blocks, kSweepThreads, 0, st>>>(S.dev, f);
+  B200_CUDA(cudaGetLastError());
+  h->launches++;
+  int32_t * hs = S.h_i.p + no + np;
+  B200_CUDA(cudaMemcpyAsync(hs, S.d_fine_sums.p, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  for (int p = 0; p < S.npairs; ++p) {
+    if (done[p]) continue;
+    response[p] = host_epilogue(h->p, fg[p], h->probs_side, fp[p], hs + (size_t)p * P * nA, S.do_penalize, &mean[3 * p], &cov[9 * p]);
+  }
+  return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define B200_GUARD_BEGIN try {
+#define B200_GUARD_END                                                     \
+  }                                                                        \
+  catch (const b200::CudaFail & f) { return f.code; }                      \
+  catch (const std::bad_alloc &) { b200::set_last_error("out of host memory"); return B200_ERR_CUDA; } \
+  catch (const std::exception & e) { b200::set_last_error(e.what()); return B200_ERR_CUDA; }
+
+extern "C" {
+
+int b200sm_batch_upload(b200sm * h, const b200_scan * queries, int32_t nq, const b200_scan * scans, int32_t nscans,
+                        const int32_t * chain_start, int32_t nchains, const int32_t * pair_query,
+                        const int32_t * pair_chain, int32_t npairs, int32_t do_penalize)
+{
+  B200_GUARD_BEGIN
+  if (!h) return B200_ERR_INVALID_ARG;
+  return sweep_upload(h, queries, nq, scans, nscans, chain_start, nchains, pair_query, pair_chain, npairs, do_penalize != 0);
+  B200_GUARD_END
+}
+
+int b200sm_batch_run(b200sm * h)
+{
+  B200_GUARD_BEGIN
+  if (!h) return B200_ERR_INVALID_ARG;
+  return sweep_run(h);
+  B200_GUARD_END
+}
+
+int b200sm_batch_fetch(b200sm * h, double * response, double * mean, double * cov)
+{
+  B200_GUARD_BEGIN
+  if (!h) return B200_ERR_INVALID_ARG;
+  return sweep_fetch(h, false, response, mean, cov);
+  B200_GUARD_END
+}
+
+int b200sm_batch_kernel_ms(b200sm * h, float * ms)
+{
+  B200_GUARD_BEGIN
+  if (!h || !ms || !h->sweep.ran) return B200_ERR_INVALID_ARG;
+  B200_CUDA(cudaEventSynchronize(h->sweep.ev1));
+  B200_CUDA(cudaEventElapsedTime(ms, h->sweep.ev0, h->sweep.ev1));
+  return B200_OK;
+  B200_GUARD_END
+}
+
+int b200sm_batch_best(b200sm * h, int32_t * best_sum, int32_t * best_index, int32_t * tie_count)
+{
+  B200_GUARD_BEGIN
+  if (!h || !h->sweep.ran) return B200_ERR_INVALID_ARG;
+  SweepHost & S = h->sweep;
+  B200_CUDA(cudaMemcpyAsync(S.h_out.p, S.d_out.p, (size_t)S.npairs * sizeof(PairOut), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  for (int p = 0; p < S.npairs; ++p) {
+    if (best_sum) best_sum[p] = S.h_out.p[p].best_sum;
+    if (best_index) best_index[p] = S.h_out.p[p].tie_count > 0 ? S.h_out.p[p].ties[0] : -1;
+    if (tie_count) tie_count[p] = S.h_out.p[p].tie_count;
+  }
+  return B200_OK;
+  B200_GUARD_END
+}
+
+int b200sm_match_batch(b200sm * h, const b200_scan * queries, int32_t nq, const b200_scan * scans, int32_t nscans,
+                       const int32_t * chain_start, int32_t nchains, const int32_t * pair_query,
+                       const int32_t * pair_chain, int32_t npairs, int32_t do_penalize, int32_t do_refine,
+                       double * response, double * mean, double * cov)
+{
+  B200_GUARD_BEGIN
+  if (!h) return B200_ERR_INVALID_ARG;
+  int rc = sweep_upload(h, queries, nq, scans, nscans, chain_start, nchains, pair_query, pair_chain, npairs, do_penalize != 0);
+  if (rc != B200_OK) return rc;
+  rc = sweep_run(h);
+  if (rc != B200_OK) return rc;
+  return sweep_fetch(h, do_refine != 0, response, mean, cov);
+  B200_GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,180 @@
+// Data structures of the scan matcher shared between scan_matcher.cu (single-match path, C ABI)
+// and sm_sweep.cu (batched loop-closure sweep).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "common.cuh"
+#include "sm_math.cuh"
+
+namespace b200 {
+
+constexpr int kMaxTies = 24;          // tie indices returned per pair; more -> host re-runs the pair
+constexpr int kSweepThreads = 512;
+constexpr int32_t kDevInvalid = -(1 << 30);   // device lookup sentinel: pos + it is always < 0
+
+// CorrelationGrid geometry (M.h:1074-1313, K.h:4572-4965) + smear kernel
+struct GridGeom {
+  int width = 0, height = 0, stride = 0;
+  int roi_x = 0, roi_y = 0, roi_w = 0, roi_h = 0;
+  int data_size = 0;
+  int ksize = 0;
+  bool order_dependent = false;     // kernel has 100s off-centre (hard part 2)
+  double scale = 0.0;
+  double off_x = 0.0, off_y = 0.0;  // CoordinateConverter offset of the last raster
+  std::vector<uint8_t> kernel;
+};
+
+// One CorrelateScan pass prepared on the host (see build_plan)
+struct CorrPlan {
+  bool fine = false;
+  int nX = 0, nY = 0, nA = 0, n = 0;
+  double center[3] = {0, 0, 0}, sp_off[2] = {0, 0}, sp_res[2] = {0, 0}, ang_off = 0, ang_res = 0;
+  std::vector<int32_t> offsets;            // nA x n, reference linear offsets (INVALID_SCAN kept)
+  std::vector<int32_t> xs, ys;             // grid column / row (ROI included) per x / y index
+  std::vector<int32_t> px, py;             // search-space-probability grid cell per x / y index
+  std::vector<double> xrel, yrel;          // m_xPoses / m_yPoses
+  std::vector<double> newx, newy;          // searchCenter + x / y
+  std::vector<double> sqx, sqy;            // Square(x) / Square(y)
+  std::vector<double> angle, heading, angpen;   // raw angle, NormalizeAngle(angle), angle penalty
+};
+
+int build_plan(const GridGeom & g, int probs_side, const b200sm_params & prm, const b200_scan * q,
+               const double center[3], const double sp_off[2], const double sp_res[2], double ang_off,
+               double ang_res, bool fine, CorrPlan & pl);
+
+// tail of ComputePositionalCovariance (M.cpp:935-965) from the accumulated sums
+inline void finish_positional_cov(double norm, double aXX, double aXY, double aYY, double best,
+                                  const double sp_res[2], double ang_res, double cov[9])
+{
+  if (norm > kTolerance) {
+    double vXX = aXX / norm, vXY = aXY / norm, vYY = aYY / norm;
+    double vTT = 4 * square(ang_res);
+    double minXX = 0.1 * square(sp_res[0]), minYY = 0.1 * square(sp_res[1]);
+    vXX = maximum(vXX, minXX);
+    vYY = maximum(vYY, minYY);
+    double mult = 1.0 / best;
+    cov[0] = vXX * mult; cov[1] = vXY * mult; cov[3] = vXY * mult; cov[4] = vYY * mult; cov[8] = vTT;
+  }
+  if (double_equal(cov[0], 0.0)) cov[0] = kMaxVariance;
+  if (double_equal(cov[4], 0.0)) cov[4] = kMaxVariance;
+}
+
+// per-pair result of the device reduction
+struct PairOut {
+  double best;              // best response (before the <= 1 clamp)
+  double avg_x, avg_y;      // mean position of the tied poses
+  double norm, acc_xx, acc_xy, acc_yy;   // ComputePositionalCovariance accumulators
+  int32_t best_sum;         // best integer correlation sum
+  int32_t tie_count;
+  int32_t ties[kMaxTies];   // flat pose indices (y*nX+x)*nA+a of the first ties, array order
+};
+
+// everything the sweep kernels read, by value
+struct SweepDev {
+  // geometry
+  int stride, roi_x, roi_y, roi_w, roi_h, data_size, ksize, order_dependent;
+  double scale;
+  const uint8_t * kern;
+  // search space (coarse pass; same for every query)
+  int nX, nY, nA, n;
+  double norm;                   // n * 100
+  int do_penalize;
+  double dist_var, min_dist_pen;
+  // per query
+  const int32_t * offsets;       // [nq][nA][n] device-form lookup
+  const int32_t * posidx;        // [nq][nY*nX]
+  const double * qgeom;          // [nq][4] viewpoint x,y, grid offset x,y
+  const double * center;         // [nq][3]
+  const double * xrel, * yrel, * newx, * newy, * sqx, * sqy;   // [nq][nX] / [nq][nY]
+  const double * angpen;         // [nq][nA]
+  // candidates
+  const double * points;         // all candidate scans' unfiltered points, x,y interleaved
+  const int32_t * scan_pt_start; // [nscans+1]
+  // pairs / items (item = one scan of one pair's chain)
+  int npairs, nitems, max_n;
+  const int32_t * pair_query;    // [npairs]
+  const int32_t * pair_item_start;   // [npairs+1]
+  const int32_t * item_pair, * item_scan;   // [nitems]
+  int32_t * cells;               // [nitems][max_n]
+  int32_t * cell_count;          // [nitems]
+  // per-CTA workspaces
+  uint8_t * ws_grid; size_t ws_grid_pitch;
+  int32_t * ws_sums; size_t ws_sums_pitch;
+  double * ws_probs; size_t ws_probs_pitch;   // P probs + 4P covariance terms
+  PairOut * out;
+};
+
+struct FineDev {
+  int P, nA;
+  const int32_t * offsets;   // [npairs][nA][n]
+  const int32_t * posidx;    // [npairs][P]
+  int32_t * sums;            // [npairs][P*nA]
+};
+
+// host state of an uploaded sweep
+struct SweepHost {
+  bool uploaded = false, ran = false;
+  int nq = 0, npairs = 0, nitems = 0, nscans = 0, max_n = 0, n = 0, blocks = 0;
+  bool do_penalize = false;
+  std::vector<CorrPlan> plans;             // one coarse plan per query
+  std::vector<int32_t> pair_query, pair_chain;
+  // copies of what the fine pass / fallbacks need from the caller's arrays
+  std::vector<b200_scan> queries, scans;
+  std::vector<int32_t> chain_start;
+  DevBuf<int32_t> d_offsets, d_posidx, d_scan_pt_start, d_pair_query, d_pair_item_start, d_item_pair, d_item_scan,
+    d_cells, d_cell_count, d_ws_sums, d_fine_off, d_fine_pos, d_fine_sums;
+  DevBuf<double> d_qgeom, d_center, d_qd, d_angpen, d_points, d_ws_probs;
+  DevBuf<uint8_t> d_ws_grid, d_kernel;
+  DevBuf<PairOut> d_out;
+  PinBuf<PairOut> h_out;
+  PinBuf<int32_t> h_i;
+  PinBuf<double> h_d;
+  SweepDev dev{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void release();
+};
+
+}  // namespace b200
+
+// the opaque handle of include/b200slam.h
+struct b200sm {
+  b200sm_params p{};
+  b200::GridGeom g;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  int probs_side = 0;   // Grid<double> m_pSearchSpaceProbs side (M.cpp:513)
+
+  // single-match device state
+  b200::DevBuf<uint8_t> d_grid, d_kernel;
+  b200::DevBuf<int32_t> d_cells, d_offsets, d_sums;
+  b200::PinBuf<int32_t> h_stage_i, h_sums;
+  bool have_raster = false;
+
+  b200::SweepHost sweep;
+
+  void ensure_stream()
+  {
+    if (!stream) {
+      B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      own_stream = true;
+    }
+  }
+};
+
+namespace b200 {
+// single-match entry used by the sweep for pairs the device reduction cannot finish
+// (tie-list overflow, response expansion)
+double do_match(b200sm * h, const b200_scan * query, const b200_scan * base, int nbase, bool pen, bool refine,
+                double mean[3], double cov[9]);
+int32_t device_offset(int32_t off, int data_size);
+void set_grid_offset(GridGeom & g, const b200_scan * query);
+double normalize_angle_difference(double minuend, double subtrahend);
+}  // namespace b200
+
+namespace b200 {
+// ScanMatcher::CorrelateScan's reduction + covariance (M.cpp:775-1025) on the host from an integer volume
+double host_epilogue(const b200sm_params & prm, const GridGeom & geom, int probs_side, const CorrPlan & pl,
+                     const int32_t * sums, bool do_penalize, double mean[3], double cov[9]);
+}  // namespace b200

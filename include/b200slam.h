@@ -134,6 +134,14 @@ int b200sm_batch_kernel_ms(b200sm * h, float * ms);
 /* per-pair best integer correlation sum and the flat index (y*nX+x)*nA+a of its first
  * arg-max pose from the last run (parity: "integer correlation-grid indices bit-exact") */
 int b200sm_batch_best(b200sm * h, int32_t * best_sum, int32_t * best_index, int32_t * tie_count);
+/* Multi-GPU sweep: writes, for each of the nq queries, the packed key
+ *   (best integer correlation sum << 32) | (0xFFFFFFFF - (id_offset + chain index))
+ * of this rank's best candidate into device_keys (nq uint64 in DEVICE memory, e.g. the buffer the
+ * caller hands to ncclAllReduce(ncclMax) / torch.distributed.all_reduce(MAX) next), on the
+ * handle's stream. A max over ranks selects the highest sum, ties to the lowest global id. */
+int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset);
+/* bytes copied host->device by upload and device->host by fetch since the last reset */
+int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_bytes, int32_t reset);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t b200sm_launch_count(const b200sm * h);
 

@@ -96,6 +96,8 @@ def lib():
     L.b200sm_batch_fetch.argtypes = [C.c_void_p, _DP, _DP, _DP]
     L.b200sm_batch_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.b200sm_batch_best.argtypes = [C.c_void_p, _IP, _IP, _IP]
+    L.b200sm_batch_reduce_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.b200sm_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]
     L.b200sm_launch_count.restype = C.c_int64
     L.b200sm_launch_count.argtypes = [C.c_void_p]
     if hasattr(L, "b200pg_create"):
@@ -318,6 +320,15 @@ class ScanMatcher:
         s, i, t = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
         _check(lib().b200sm_batch_best(self._h, _ip(s), _ip(i), _ip(t)))
         return s, i, t
+
+    def batch_reduce_keys(self, device_ptr: int, id_offset: int = 0):
+        """Per-query packed best-response keys into a device buffer (see b200sm_batch_reduce_keys)."""
+        _check(lib().b200sm_batch_reduce_keys(self._h, C.c_void_p(device_ptr), int(id_offset)))
+
+    def transfer_bytes(self, reset: bool = False):
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().b200sm_batch_transfer_bytes(self._h, C.byref(a), C.byref(b), int(reset)))
+        return a.value, b.value
 
     def launch_count(self) -> int:
         return int(lib().b200sm_launch_count(self._h))

@@ -349,6 +349,20 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_fine(SweepDev d, FineDe
 }
 
 
+// Per-query best-response key for the multi-GPU sweep: key = best_sum << 32 | (0xFFFFFFFF - global
+// candidate id), so that a max-reduction (here atomicMax, across GPUs ncclMax) picks the highest
+// integer correlation sum and breaks ties towards the lowest candidate id, deterministically.
+__global__ void k_best_keys(const PairOut * __restrict__ out, const int32_t * __restrict__ pair_query,
+                            const int32_t * __restrict__ pair_chain, int npairs, long long id_offset,
+                            unsigned long long * __restrict__ keys)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  const unsigned long long id = (unsigned long long)(id_offset + pair_chain[p]) & 0xFFFFFFFFull;
+  const unsigned long long key = ((unsigned long long)(uint32_t)out[p].best_sum << 32) | (0xFFFFFFFFull - id);
+  atomicMax(keys + pair_query[p], key);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -361,11 +375,14 @@ void SweepHost::release()
   uploaded = ran = false;
 }
 
+static thread_local int64_t * g_h2d_counter = nullptr;
+
 template <class T>
 static void h2d(DevBuf<T> & dst, const T * src, size_t count, cudaStream_t s)
 {
   dst.reserve(count);
   if (count) B200_CUDA(cudaMemcpyAsync(dst.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  if (g_h2d_counter) *g_h2d_counter += (int64_t)(count * sizeof(T));
 }
 
 static GridGeom geom_for_query(const b200sm * h, const b200_scan * q)
@@ -393,6 +410,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
 {
   SweepHost & S = h->sweep;
   S.uploaded = S.ran = false;
+  g_h2d_counter = &S.h2d_bytes;
   if (!queries || nq <= 0 || !scans || nscans <= 0 || !chain_start || nchains <= 0) {
     set_last_error("sweep: empty or NULL input");
     return B200_ERR_INVALID_ARG;
@@ -489,11 +507,13 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   if (contiguous) {
     // caller laid the scans out back to back (pinned or not): one copy straight from its buffer
     B200_CUDA(cudaMemcpyAsync(S.d_points.p, scans[0].points_xy, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    S.h2d_bytes += (int64_t)(2 * npts * sizeof(double));
   } else {
     S.h_d.reserve(2 * npts);
     for (int s = 0; s < nscans; ++s)
       std::memcpy(S.h_d.p + 2 * (size_t)pt_start[s], scans[s].points_xy, 2 * (size_t)scans[s].n * sizeof(double));
     B200_CUDA(cudaMemcpyAsync(S.d_points.p, S.h_d.p, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    S.h2d_bytes += (int64_t)(2 * npts * sizeof(double));
   }
   S.max_n = std::max(max_n, 1);
 
@@ -521,6 +541,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
     }
     h2d(S.d_scan_pt_start, a_pt, nscans + 1, st);
     h2d(S.d_pair_query, a_pq, npairs, st);
+    h2d(S.d_pair_chain, S.pair_chain.data(), npairs, st);
     h2d(S.d_pair_item_start, a_pis, npairs + 1, st);
     h2d(S.d_item_pair, a_ip, std::max(nitems, 1), st);
     h2d(S.d_item_scan, a_is, std::max(nitems, 1), st);
@@ -638,6 +659,7 @@ static int sweep_fetch(b200sm * h, bool do_refine, double * response, double * m
   cudaStream_t st = h->stream;
   B200_CUDA(cudaMemcpyAsync(S.h_out.p, S.d_out.p, (size_t)S.npairs * sizeof(PairOut), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
+  S.d2h_bytes += (int64_t)((size_t)S.npairs * sizeof(PairOut));
   std::vector<char> done(S.npairs, 0);
   for (int p = 0; p < S.npairs; ++p) {
     if (!finish_pair(h, S, p, S.h_out.p[p], &response[p], &mean[3 * p], &cov[9 * p])) {
@@ -686,6 +708,7 @@ static int sweep_fetch(b200sm * h, bool do_refine, double * response, double * m
   h->launches++;
   int32_t * hs = S.h_i.p + no + np;
   B200_CUDA(cudaMemcpyAsync(hs, S.d_fine_sums.p, ns * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  S.d2h_bytes += (int64_t)(ns * sizeof(int32_t));
   B200_CUDA(cudaStreamSynchronize(st));
   for (int p = 0; p < S.npairs; ++p) {
     if (done[p]) continue;
@@ -757,6 +780,29 @@ int b200sm_batch_best(b200sm * h, int32_t * best_sum, int32_t * best_index, int3
   }
   return B200_OK;
   B200_GUARD_END
+}
+
+int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset)
+{
+  B200_GUARD_BEGIN
+  if (!h || !device_keys || !h->sweep.ran) return B200_ERR_INVALID_ARG;
+  SweepHost & S = h->sweep;
+  B200_CUDA(cudaMemsetAsync(device_keys, 0, (size_t)S.nq * sizeof(unsigned long long), h->stream));
+  k_best_keys<<<(S.npairs + 255) / 256, 256, 0, h->stream>>>(S.d_out.p, S.d_pair_query.p, S.d_pair_chain.p, S.npairs,
+                                                            (long long)id_offset, static_cast<unsigned long long *>(device_keys));
+  B200_CUDA(cudaGetLastError());
+  h->launches++;
+  return B200_OK;
+  B200_GUARD_END
+}
+
+int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_bytes, int32_t reset)
+{
+  if (!h) return B200_ERR_INVALID_ARG;
+  if (h2d_bytes) *h2d_bytes = h->sweep.h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = h->sweep.d2h_bytes;
+  if (reset) h->sweep.h2d_bytes = h->sweep.d2h_bytes = 0;
+  return B200_OK;
 }
 
 int b200sm_match_batch(b200sm * h, const b200_scan * queries, int32_t nq, const b200_scan * scans, int32_t nscans,

@@ -122,7 +122,7 @@ struct SweepHost {
   // copies of what the fine pass / fallbacks need from the caller's arrays
   std::vector<b200_scan> queries, scans;
   std::vector<int32_t> chain_start;
-  DevBuf<int32_t> d_offsets, d_posidx, d_scan_pt_start, d_pair_query, d_pair_item_start, d_item_pair, d_item_scan,
+  DevBuf<int32_t> d_offsets, d_posidx, d_scan_pt_start, d_pair_query, d_pair_chain, d_pair_item_start, d_item_pair, d_item_scan,
     d_cells, d_cell_count, d_ws_sums, d_fine_off, d_fine_pos, d_fine_sums;
   DevBuf<double> d_qgeom, d_center, d_qd, d_angpen, d_points, d_ws_probs;
   DevBuf<uint8_t> d_ws_grid, d_kernel;
@@ -132,6 +132,7 @@ struct SweepHost {
   PinBuf<double> h_d;
   SweepDev dev{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes moved by upload / fetch since the last reset
   void release();
 };
 

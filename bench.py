@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark of b200slam (contract: task brief, section 4).
+
+Metric (BASELINE.json): scan matches/sec (1081-beam, +-2 m / +-20 deg) on the loop-closure
+batch workload (configs[1]: 1 query x 1000 candidate 1081-beam scans per GPU), plus the
+10k-node / 40k-edge SE(2) pose-graph solve time (configs[3]) reported in the same JSON line
+under "graph_solve".
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
+                                                           # (oracle/_ref = unmodified karto_sdk)
+
+One "step" = one pass of the hot path over one batch: every rank sweeps its shard of candidate
+chains (rasterise + exhaustive (x, y, theta) correlation + reduction for each (query, chain)
+pair) and, for N > 1, joins the per-query best-response all-reduce (NCCL, MAX of a packed key).
+  value  : pairs matched by all ranks / device time, inputs already resident in HBM
+  e2e    : the same through the public API call (ScanMatcher.MatchScanBatch) with HOST inputs
+           (pinned), host<->device copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "scan matches/sec (1081-beam, +-2m/+-20deg)"
+UNIT = "matches/s"
+
+# cfg2 / cfg5 parameters: loop matcher, search 4.0 m @ 0.05 m, smear 0.03, +-20 deg / 2 deg
+LOOP_GRID = (4.0, 0.05, 0.03, 12.0)
+LOOP_MAPPER = dict(coarse_search_angle_offset=math.radians(20.0), coarse_angle_resolution=math.radians(2.0),
+                   fine_search_angle_offset=math.radians(0.2), distance_variance_penalty=0.5, angle_variance_penalty=1.0,
+                   minimum_distance_penalty=0.5, minimum_angle_penalty=0.9, use_response_expansion=0)
+N_CAND = 1000       # candidate chains per GPU per step
+CHAIN_LEN = 1
+N_QUERY = 1
+GRAPH_NODES, GRAPH_EDGES = 10000, 40000
+GRAPH_SIGMA = (0.03, 0.01)
+
+
+def algorithmic_bytes_per_match(n_beams: int, n_angles: int, npairs: int, nq: int) -> float:
+    """compulsory bytes of one LOOP coarse match = the 320,920 B correlation grid it
+    is matched against + 128 B of outputs + the query's lookup table (n_angles x n_beams int32)
+    amortised over the pairs that share it."""
+    grid_bytes = 568 * 565
+    return grid_bytes + 128 + (n_angles * n_beams * 4) * nq / max(npairs, 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(rank: int, n_cand: int, chain_len: int, n_query: int):
+    from slam_toolbox_b200 import synth
+    # same world + queries on every rank, candidates differ per rank (sharded candidate set)
+    world = synth.make_world(7)
+    rng = np.random.default_rng(1234)
+    qtrue = np.array([synth.free_pose(world, rng) for _ in range(n_query)])
+    qranges = synth.noisy(synth.raycast(world, qtrue), rng)
+    qpose = qtrue + np.column_stack([rng.normal(0, 0.5, (n_query, 2)), rng.normal(0, 0.08, n_query)])
+    crng = np.random.default_rng(99 + rank)
+    starts = synth.poses_near(world, qtrue[0, :2], 3.0, n_cand, crng)
+    cposes = starts if chain_len == 1 else np.concatenate([synth.chain_poses(world, s, chain_len, crng) for s in starts])
+    cranges = synth.noisy(synth.raycast(world, cposes), crng)
+    chain_start = np.arange(0, n_cand * chain_len + 1, chain_len, dtype=np.int32)
+    return qranges, qpose, cranges, cposes, chain_start
+
+
+def cpu_sweep(qranges, qpose, cranges, cposes, chain_start, n_sample: int, threads: int):
+    """The reference's own MatchScan (oracle/_ref, unmodified karto_sdk) over the first n_sample chains,
+    one reference ScanMatcher per host thread. Returns (matches/s, kind, seconds, responses)."""
+    from oracle import karto_ref as R
+    from oracle import karto_port as P
+    from slam_toolbox_b200 import synth
+    n_sample = min(n_sample, len(chain_start) - 1)
+    cs = chain_start[:n_sample + 1]
+    if R.available():
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)   # the reference prints "Registering sensor" to stdout
+        try:
+            R.init_laser(synth.ANGLE_MIN, synth.ANGLE_MAX, synth.ANGLE_INC, 0.1, 30.0, LOOP_GRID[3])
+        finally:
+            os.dup2(saved, 1); os.close(devnull); os.close(saved)
+        mp = R.RefMapper(**LOOP_MAPPER)
+        matchers = [R.RefMatcher(mp, *LOOP_GRID) for _ in range(threads)]
+        q = R.RefScan(qranges[0], qpose[0], 100000)
+        scans = [R.RefScan(cranges[i], cposes[i], i) for i in range(cs[-1])]
+        sec, resp, _, _ = R.sweep(matchers, q, scans, cs, False, False)
+        return n_sample / sec, "reference", sec, resp
+    # port fallback (single thread): the plain-C restatement
+    pm = P.PortMatcher(search_size=LOOP_GRID[0], resolution=LOOP_GRID[1], smear_deviation=LOOP_GRID[2], range_threshold=LOOP_GRID[3],
+                       coarse_search_angle_offset=LOOP_MAPPER["coarse_search_angle_offset"],
+                       coarse_angle_resolution=LOOP_MAPPER["coarse_angle_resolution"],
+                       fine_search_angle_offset=LOOP_MAPPER["fine_search_angle_offset"], distance_variance_penalty=0.25,
+                       angle_variance_penalty=1.0, minimum_distance_penalty=0.5, minimum_angle_penalty=0.9, use_response_expansion=0)
+    q = P.PortScan(qranges[0], qpose[0], synth.ANGLE_MIN, synth.ANGLE_INC)
+    scans = [P.PortScan(cranges[i], cposes[i], synth.ANGLE_MIN, synth.ANGLE_INC) for i in range(cs[-1])]
+    t = time.perf_counter()
+    resp = [pm.match(q, scans[cs[j]:cs[j + 1]], False, False)[0] for j in range(n_sample)]
+    sec = time.perf_counter() - t
+    return n_sample / sec, "port", sec, np.array(resp)
+
+
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    threads = host_threads()
+    qr, qp, cr, cp, cs = make_inputs(0, N_CAND, CHAIN_LEN, N_QUERY)
+    # bounded sample per step: ~2-4 s of CPU work
+    n_sample = min(N_CAND, max(16, 12 * threads))
+    rates = []
+    for i in range(args.warmup + args.steps):
+        rate, kind, sec, _ = cpu_sweep(qr, qp, cr, cp, cs, n_sample, threads)
+        if i >= args.warmup:
+            rates.append((rate, sec))
+    value = float(np.mean([r for r, _ in rates]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([s for _, s in rates])), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"cfg2 loop-closure batch: {N_QUERY} query x {N_CAND} candidate 1081-beam scans, +-2m/+-20deg "
+                               f"(bounded sample: first {n_sample} candidates per step)",
+                   "search": "41x41x21 poses", "grid": "565x568 u8", "threads": threads},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{n_sample} of {N_CAND} candidate matches per step, one ScanMatcher per host thread"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def graph_solve_bench(steps: int, with_cpu: bool):
+    """cfg4: 10k-node / 40k-edge Manhattan-world graph, dead-reckoned initial guess."""
+    from slam_toolbox_b200 import synth, api
+    g = synth.make_pose_graph(0, GRAPH_NODES, GRAPH_EDGES, sigma_xy=GRAPH_SIGMA[0], sigma_th=GRAPH_SIGMA[1])
+    out = {"nodes": GRAPH_NODES, "edges": int(len(g["edge_a"])), "sigma_xy": GRAPH_SIGMA[0], "sigma_th": GRAPH_SIGMA[1],
+           "init": "dead-reckoned odometry"}
+    ms, summ = [], None
+    poses = None
+    for i in range(steps + 1):   # first solve is the warm-up (allocations, cooperative-launch set-up)
+        s = api.ScanSolver()
+        for nid, p in zip(g["ids"], g["init"]):
+            s.AddNode(int(nid), p)
+        for a, b, z, c in zip(g["edge_a"], g["edge_b"], g["z"], g["cov"]):
+            s.AddConstraint(int(a), int(b), z, c)
+        t = time.perf_counter()
+        ok = s.Compute()
+        wall = (time.perf_counter() - t) * 1e3
+        summ = s.summary
+        if i > 0:
+            ms.append((summ.solve_ms, wall))
+        poses = s.GetCorrections()[1]
+        s.close()
+    out.update({"ms": float(np.mean([m for m, _ in ms])), "wall_ms": float(np.mean([w for _, w in ms])), "usable": bool(ok),
+                "lm_iterations": int(summ.iterations), "pcg_iterations": int(summ.pcg_iterations), "final_cost": float(summ.final_cost),
+                "kernel_launches": int(summ.kernel_launches)})
+    if with_cpu:
+        from oracle import posegraph as PG
+        t = time.perf_counter()
+        xo, so = PG.solve(g["init"], g["edge_a"], g["edge_b"], g["z"], cov=g["cov"])
+        cpu_ms = (time.perf_counter() - t) * 1e3
+        d = poses - xo
+        d[:, 2] = synth.wrap(d[:, 2])
+        out["cpu_baseline"] = {"ms": cpu_ms, "kind": "port", "cores": 1,
+                               "what": "restated Ceres LM + SciPy SuperLU exact solves (Ceres itself is not installable here)",
+                               "lm_iterations": so.iterations, "final_cost": so.final_cost}
+        out["parity_vs_oracle"] = {"max_abs_dxy_m": float(np.abs(d[:, :2]).max()), "max_abs_dtheta_rad": float(np.abs(d[:, 2]).max())}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="skip the pose-graph solve part")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--chain-len", type=int, default=CHAIN_LEN)
+    ap.add_argument("--candidates", type=int, default=N_CAND)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from slam_toolbox_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the b200 implementation has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    api._check(api.lib().b200_set_device(local_rank))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    n_cand, chain_len = args.candidates, args.chain_len
+    qr, qp, cr, cp, cs = make_inputs(rank, n_cand, chain_len, N_QUERY)
+    laser = api.LaserRangeFinder()
+    mapper = api.MapperParams(**{k: (bool(v) if k == "use_response_expansion" else v) for k, v in LOOP_MAPPER.items()})
+    sm = api.ScanMatcher.Create(mapper, *LOOP_GRID)
+    stream = torch.cuda.current_stream()
+    sm.set_stream(stream.cuda_stream)
+
+    # host inputs in pinned memory (the e2e leg copies from here every step)
+    pts_pinned = torch.empty((cr.shape[0], cr.shape[1], 2), dtype=torch.float64).pin_memory()
+    pts_np = pts_pinned.numpy()
+    pts_np[...] = api.point_readings(cr, cp, laser)
+    cands = api.ScanBlock(cr, cp, laser, points=pts_np)
+    assert cands.points.ctypes.data == pts_np.ctypes.data
+    queries = api.ScanBlock(qr, qp, laser)
+    npairs = N_QUERY * n_cand
+    keys = torch.zeros(N_QUERY, dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        sm.batch_run()
+        if world > 1:
+            sm.batch_reduce_keys(keys.data_ptr(), rank * n_cand)
+            dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+
+    # ---- device-resident leg: inputs uploaded once ----
+    sm.batch_upload(queries, cands, cs, None, False)
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = sm.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    barrier()
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)            # evict L2 between timed iterations (outside the event pair)
+        ev[k][0].record(stream)
+        device_step()
+        ev[k][1].record(stream)
+        kernel_ms.append(None)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = float(np.sum(step_ms))
+    last_kernel_ms = sm.batch_kernel_ms()
+    launches = sm.launch_count() - launches0
+    resp_dev, mean_dev, cov_dev = sm.batch_fetch()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end leg: public API, host inputs, copies inside the timed region ----
+    sm.transfer_bytes(reset=True)
+    for _ in range(2):
+        r_e2e = sm.MatchScanBatch(queries, cands, cs, None, False, False)
+        if world > 1:
+            dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+    sm.transfer_bytes(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r_e2e = sm.MatchScanBatch(queries, cands, cs, None, False, False)
+        if world > 1:
+            sm.batch_reduce_keys(keys.data_ptr(), rank * n_cand)
+            dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+            torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d, d2h = sm.transfer_bytes()
+    assert np.array_equal(r_e2e[0], resp_dev)
+
+    # max over ranks
+    t = torch.tensor([dev_ms, e2e_s * 1e3, last_kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, kern_ms = [float(v) for v in t.tolist()]
+    total_pairs = npairs * world
+    value = total_pairs * args.steps / (dev_ms * 1e-3)
+    e2e_value = total_pairs * args.steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()   # rank 0 finishes the CPU baseline / graph solve, then everyone leaves together
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the fused sweep kernel) ----
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    n_angles = int(math.floor(2 * LOOP_MAPPER["coarse_search_angle_offset"] / LOOP_MAPPER["coarse_angle_resolution"] + 0.5)) + 1
+    bytes_per_launch = algorithmic_bytes_per_match(cr.shape[1], n_angles, npairs, N_QUERY) * npairs
+    achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+    gathers = npairs * 41 * 41 * n_angles * cr.shape[1]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "k_sweep (fused raster+correlate+reduce)", "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_match": bytes_per_launch / npairs,
+                "onchip": {"gathers_per_s": gathers / (kern_ms * 1e-3), "smem_gather_ceiling_per_s": 32 * 148 * 1.9e9,
+                           "note": "the path is bound by on-chip gather/ALU issue rate, not HBM (SURVEY.md 7.5)"}}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("sweep_kernel_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- CPU baseline on the host cores (bounded sample of the same workload) ----
+    cpu = None
+    if not args.no_cpu:
+        threads = host_threads()
+        n_sample = min(n_cand, max(16, 12 * threads))
+        rate, kind, sec, resp_cpu = cpu_sweep(qr, qp, cr, cp, cs, n_sample, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"first {n_sample} of {n_cand} candidate matches, one reference ScanMatcher per host thread, {sec:.2f} s",
+               "parity_exact": bool(np.array_equal(resp_cpu, resp_dev[:n_sample]))}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"cfg2 loop-closure batch: {N_QUERY} query x {n_cand} candidate chains (chain length {chain_len}) of "
+                               f"1081-beam scans per GPU, +-2m/+-20deg window, candidates sharded over {world} GPU(s)",
+                   "search": f"41x41x{n_angles} poses", "grid": "565x568 u8 (res 0.05 m, smear 0.03 m, range threshold 12 m)",
+                   "l2": "L2 flushed between timed steps (256 MiB write)", "collective": "all_reduce(MAX) of packed best-response keys" if world > 1 else "none"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+    }
+    if not args.no_graph:
+        line["graph_solve"] = graph_solve_bench(3, not args.no_cpu)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

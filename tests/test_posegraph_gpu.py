@@ -1,0 +1,110 @@
+"""Parity of the CUDA pose-graph solver with the restated-Ceres oracle (tolerance from BASELINE.json's
+north_star: 1e-4 m / 1e-5 rad) and the ScanSolver API semantics of solvers/ceres_solver.cpp."""
+import numpy as np
+import pytest
+
+from oracle import posegraph as PG
+from slam_toolbox_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+TOL_XY, TOL_TH = 1e-4, 1e-5
+
+
+def build(g, **opts):
+    s = api.ScanSolver(**opts)
+    for nid, p in zip(g["ids"], g["init"]):
+        s.AddNode(int(nid), p)
+    for a, b, z, c in zip(g["edge_a"], g["edge_b"], g["z"], g["cov"]):
+        assert s.AddConstraint(int(a), int(b), z, c)
+    return s
+
+
+def diff(x, y):
+    d = x - y
+    d[:, 2] = synth.wrap(d[:, 2])
+    return np.abs(d[:, :2]).max(), np.abs(d[:, 2]).max()
+
+
+@pytest.mark.parametrize("n,e,seed", [(60, 120, 0), (500, 1400, 1), (3000, 9000, 2)])
+def test_solve_matches_oracle_at_reference_tolerances(n, e, seed):
+    g = synth.make_pose_graph(seed, n, e, sigma_xy=0.03, sigma_th=0.01)
+    xo, so = PG.solve(g["init"], g["edge_a"], g["edge_b"], g["z"], cov=g["cov"])
+    s = build(g)
+    assert s.Compute()
+    ids, xg = s.GetCorrections()
+    assert np.array_equal(ids, g["ids"])
+    dxy, dth = diff(xg, xo)
+    assert dxy < TOL_XY and dth < TOL_TH, (dxy, dth)
+    assert s.summary.iterations == so.iterations and s.summary.successful_steps == so.successful_steps
+    assert abs(s.summary.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    assert np.array_equal(xg[0], g["init"][0])   # first node is the constant anchor
+
+
+def test_solve_matches_oracle_at_tight_tolerances():
+    g = synth.make_pose_graph(5, 400, 1100, sigma_xy=0.03, sigma_th=0.01)
+    kw = dict(function_tolerance=1e-14, parameter_tolerance=1e-13, gradient_tolerance=1e-13, max_num_iterations=100)
+    xo, so = PG.solve(g["init"], g["edge_a"], g["edge_b"], g["z"], cov=g["cov"], opts=PG.Options(**kw))
+    s = build(g, pcg_tolerance=1e-13, **kw)
+    assert s.Compute()
+    dxy, dth = diff(s.GetCorrections()[1], xo)
+    assert dxy < 1e-6 and dth < 1e-6, (dxy, dth)
+
+
+def test_cfg4_full_size():
+    g = synth.make_pose_graph(0, 10000, 40000, sigma_xy=0.03, sigma_th=0.01)
+    xo, so = PG.solve(g["init"], g["edge_a"], g["edge_b"], g["z"], cov=g["cov"])
+    s = build(g)
+    assert s.Compute()
+    dxy, dth = diff(s.GetCorrections()[1], xo)
+    assert dxy < TOL_XY and dth < TOL_TH, (dxy, dth)
+    # size-independent properties: cost near (3E - 3(N-1))/2 for unit-variance whitened residuals; re-solve converges at once
+    assert 0.8 < s.summary.final_cost / (0.5 * (3 * 40000 - 3 * 9999)) < 1.2
+    assert s.Compute() and s.summary.iterations <= 2
+
+
+def test_api_semantics():
+    g = synth.make_pose_graph(6, 50, 90, sigma_xy=0.03, sigma_th=0.01)
+    s = build(g)
+    assert s.num_nodes() == 50
+    # unknown / identical nodes are refused, state unchanged (ceres_solver.cpp:351-358)
+    ne = s.num_edges()
+    assert not s.AddConstraint(0, 999, g["z"][0], g["cov"][0]) and not s.AddConstraint(3, 3, g["z"][0], g["cov"][0])
+    assert s.num_edges() == ne
+    assert len(s.GetCorrections()[0]) == 0          # nothing before Compute
+    assert s.Compute()
+    assert len(s.GetCorrections()[0]) == 50
+    s.Clear()
+    assert len(s.GetCorrections()[0]) == 0 and s.num_nodes() == 50
+    # ModifyNode adds the stored yaw (ceres_solver.cpp:457-459)
+    before = s.get_node(7)
+    s.ModifyNode(7, [1.0, 2.0, 0.25])
+    after = s.get_node(7)
+    assert after[0] == 1.0 and after[1] == 2.0 and after[2] == 0.25 + before[2]
+    assert s.GetNodeOrientation(7) == after[2] and s.GetNodeOrientation(12345) is None
+    # RemoveConstraint in either orientation, RemoveNode drops its edges
+    a, b = int(g["edge_a"][5]), int(g["edge_b"][5])
+    assert s.RemoveConstraint(b, a) and not s.RemoveConstraint(b, a)
+    ne = s.num_edges()
+    assert s.RemoveNode(20) and not s.RemoveNode(20)
+    assert s.num_nodes() == 49 and s.num_edges() < ne
+    assert s.Compute() and len(s.GetCorrections()[0]) == 49
+    # an isolated node is not part of the problem and comes back unchanged
+    s.AddNode(777, [9.0, 9.0, 0.5])
+    assert s.Compute()
+    ids, poses = s.GetCorrections()
+    assert np.array_equal(poses[list(ids).index(777)], [9.0, 9.0, 0.5])
+    s.Reset()
+    assert s.num_nodes() == 0 and s.num_edges() == 0 and len(s.GetCorrections()[0]) == 0
+
+
+def test_removed_graph_equals_freshly_built_graph():
+    g = synth.make_pose_graph(8, 120, 300, sigma_xy=0.03, sigma_th=0.01)
+    keep = np.ones(len(g["edge_a"]), dtype=bool)
+    keep[150:170] = False
+    s1 = build(g)
+    for k in np.nonzero(~keep)[0]:
+        assert s1.RemoveConstraint(int(g["edge_a"][k]), int(g["edge_b"][k]))
+    g2 = dict(g, edge_a=g["edge_a"][keep], edge_b=g["edge_b"][keep], z=g["z"][keep], cov=g["cov"][keep])
+    s2 = build(g2)
+    assert s1.Compute() and s2.Compute()
+    assert np.array_equal(s1.GetCorrections()[1], s2.GetCorrections()[1])   # deterministic, no atomics

@@ -79,7 +79,8 @@ typedef struct b200sm b200sm;
  * (smear deviation outside [0.5, 10] * resolution, Mapper.h:1226-1235). */
 int b200sm_create(const b200sm_params * params, b200sm ** out);
 void b200sm_destroy(b200sm * h);
-/* Run this handle's kernels on an existing cudaStream_t (e.g. the caller's current stream). */
+/* Run this handle's kernels on an existing cudaStream_t (e.g. the caller's current stream).
+ * NULL (the legacy default stream) = go back to a stream owned by the handle. */
 int b200sm_set_stream(b200sm * h, void * cuda_stream);
 
 /* ScanMatcher::MatchScan(pScan, rBaseScans, rMean, rCovariance, doPenalize, doRefineMatch)
@@ -142,6 +143,9 @@ int b200sm_batch_best(b200sm * h, int32_t * best_sum, int32_t * best_index, int3
 int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset);
 /* bytes copied host->device by upload and device->host by fetch since the last reset */
 int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_bytes, int32_t reset);
+/* Tuning / testing switches. "force_generic_sweep" = 1 runs batched sweeps on the generic kernel even
+ * where the shared-memory fast path applies (both produce identical results). */
+int b200sm_set_option(b200sm * h, const char * name, int32_t value);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t b200sm_launch_count(const b200sm * h);
 

@@ -98,6 +98,7 @@ def lib():
     L.b200sm_batch_best.argtypes = [C.c_void_p, _IP, _IP, _IP]
     L.b200sm_batch_reduce_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.b200sm_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]
+    L.b200sm_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
     L.b200sm_launch_count.restype = C.c_int64
     L.b200sm_launch_count.argtypes = [C.c_void_p]
     if hasattr(L, "b200pg_create"):
@@ -283,6 +284,7 @@ class ScanMatcher:
         pq, pc, npairs = self._pairs(pairs)
         if pq is None:
             npairs = len(queries) * nch
+        self._npairs = npairs
         resp, mean, cov = np.zeros(npairs), np.zeros((npairs, 3)), np.zeros((npairs, 9))
         _check(lib().b200sm_match_batch(self._h, queries.c, len(queries), candidates.c, len(candidates), _ip(cs), nch,
                                         _ip(pq), _ip(pc), npairs, int(doPenalize), int(doRefineMatch), _dp(resp), _dp(mean),
@@ -329,6 +331,9 @@ class ScanMatcher:
         a, b = C.c_int64(), C.c_int64()
         _check(lib().b200sm_batch_transfer_bytes(self._h, C.byref(a), C.byref(b), int(reset)))
         return a.value, b.value
+
+    def set_option(self, name: str, value: int):
+        _check(lib().b200sm_set_option(self._h, name.encode(), int(value)))
 
     def launch_count(self) -> int:
         return int(lib().b200sm_launch_count(self._h))

@@ -253,6 +253,8 @@ int build_plan(const GridGeom & g, int probs_side, const b200sm_params & prm, co
   const int n = pl.n;
   // ---- lookup table ----
   pl.offsets.assign((size_t)pl.nA * n, kInvalidScan);
+  pl.ogx.assign((size_t)pl.nA * n, 0);
+  pl.ogy.assign((size_t)pl.nA * n, 0);
   double m00, m01, m02, m10, m11, m12, tx, ty, th;
   const double * sp = q->sensor_pose;
   if (sp[0] == 0.0 && sp[1] == 0.0 && sp[2] == 0.0) {   // Transform::SetTransform, K.h:3004-3009
@@ -291,6 +293,8 @@ int build_plan(const GridGeom & g, int probs_side, const b200sm_params & prm, co
       int gy = world_to_grid(oy + g.off_y, g.off_y, g.scale);
       // Grid<T>::GridIndex(gridPoint, false) in 32-bit arithmetic like the reference (K.h:4692)
       out[i] = (int32_t)((uint32_t)gx + (uint32_t)gy * (uint32_t)g.stride);
+      pl.ogx[(size_t)a * n + i] = gx;
+      pl.ogy[(size_t)a * n + i] = gy;
     }
   }
   // ---- pose arrays ----
@@ -719,5 +723,13 @@ int b200sm_grid_copy(b200sm * h, uint8_t * out, int32_t cap)
 }
 
 int64_t b200sm_launch_count(const b200sm * h) { return h ? h->launches : 0; }
+
+int b200sm_set_option(b200sm * h, const char * name, int32_t value)
+{
+  if (!h || !name) return B200_ERR_INVALID_ARG;
+  if (std::string(name) == "force_generic_sweep") { h->force_generic = value != 0; return B200_OK; }
+  set_last_error(std::string("unknown option ") + name);
+  return B200_ERR_INVALID_ARG;
+}
 
 }  // extern "C"

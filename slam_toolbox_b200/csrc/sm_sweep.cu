@@ -25,12 +25,19 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------
 
 // ScanMatcher::FindValidPoints (M.cpp:1113-1164) + WorldToGrid + ROI test (M.cpp:1082-1088) for
-// every (pair, scan of its chain): one thread walks one scan's points in order.
+// every (pair, scan of its chain).  One WARP per scan: lanes load 32 points at a time (coalesced),
+// every lane then replays the sequential state machine on them through shuffles (identical state in
+// all lanes, no divergence); accepted index ranges set flags in shared memory.  A second, parallel
+// pass turns accepted points into grid cells and compacts the in-ROI ones in scan order.
 // cells[item * max_n + k] = gx | gy << 16 of the k-th point that lands inside the ROI.
-__global__ void k_find_valid(SweepDev d)
+constexpr int kFvWarps = 4;
+__global__ void __launch_bounds__(kFvWarps * 32) k_find_valid(SweepDev d)
 {
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ unsigned char s_valid_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * kFvWarps + warp;
   if (item >= d.nitems) return;
+  unsigned char * valid = s_valid_all + (size_t)warp * d.max_n;
   const int pair = d.item_pair[item];
   const int scan = d.item_scan[item];
   const int q = d.pair_query[pair];
@@ -38,21 +45,40 @@ __global__ void k_find_valid(SweepDev d)
   const double ox = d.qgeom[q * 4 + 2], oy = d.qgeom[q * 4 + 3];
   const double * pts = d.points + 2 * (size_t)d.scan_pt_start[scan];
   const int n = d.scan_pt_start[scan + 1] - d.scan_pt_start[scan];
-  int32_t * out = d.cells + (size_t)item * d.max_n;
+  for (int i = lane; i < n; i += 32) valid[i] = 0;
+  __syncwarp();
   ValidPointState st;
   st.init();
-  int cnt = 0;
-  for (int i = 0; i < n; ++i) {
-    double cx = pts[2 * i], cy = pts[2 * i + 1];
-    int lo, hi;
-    st.step(i, cx, cy, vx, vy, lo, hi);
-    for (int t = lo; t < hi; ++t) {
-      int gx = world_to_grid(pts[2 * t], ox, d.scale);
-      int gy = world_to_grid(pts[2 * t + 1], oy, d.scale);
-      if (is_up_to(gx, d.roi_w) && is_up_to(gy, d.roi_h)) out[cnt++] = gx | (gy << 16);
+  for (int base = 0; base < n; base += 32) {
+    const int mine = base + lane;
+    double px = 0.0, py = 0.0;
+    if (mine < n) { px = pts[2 * mine]; py = pts[2 * mine + 1]; }
+    const int cnt = min(32, n - base);
+    for (int k = 0; k < cnt; ++k) {
+      const double cx = __shfl_sync(0xffffffffu, px, k), cy = __shfl_sync(0xffffffffu, py, k);
+      int lo, hi;
+      st.step(base + k, cx, cy, vx, vy, lo, hi);
+      for (int t = lo + lane; t < hi; t += 32) valid[t] = 1;   // same range in every lane
     }
   }
-  d.cell_count[item] = cnt;
+  __syncwarp();
+  int32_t * out = d.cells + (size_t)item * d.max_n;
+  int total = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int t = base + lane;
+    bool keep = false;
+    int cell = 0;
+    if (t < n && valid[t]) {
+      const int gx = world_to_grid(pts[2 * t], ox, d.scale);
+      const int gy = world_to_grid(pts[2 * t + 1], oy, d.scale);
+      keep = is_up_to(gx, d.roi_w) && is_up_to(gy, d.roi_h);
+      cell = gx | (gy << 16);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[total + __popc(m & ((1u << lane) - 1))] = cell;
+    total += __popc(m);
+  }
+  if (lane == 0) d.cell_count[item] = total;
 }
 
 __device__ __forceinline__ double block_max(double v, double * scratch)
@@ -114,7 +140,17 @@ __device__ __forceinline__ double pose_response(const SweepDev & d, int q, int s
 // ComputePositionalCovariance (M.cpp:893-933) for one pair whose integer volume is in `sums`
 // (index (y*nX+x)*nA + a).  `probs` = P doubles of scratch.  Everything that needs libm
 // (heading average) is finished on the host from the tie list.
-__device__ void pair_epilogue(const SweepDev & d, int pair, int q, const int32_t * sums,
+struct SumsPoseMajor {   // generic path: volume index (y*nX + x)*nA + a in global memory
+  const int32_t * v; int nA;
+  __device__ __forceinline__ int operator()(int p, int a) const { return v[(size_t)p * nA + a]; }
+};
+struct SumsAngleMajor {  // fast path: accumulators [a][y*nX + x] in shared memory
+  const int32_t * v; int P;
+  __device__ __forceinline__ int operator()(int p, int a) const { return v[a * P + p]; }
+};
+
+template <class SumAt>
+__device__ void pair_epilogue(const SweepDev & d, int pair, int q, const SumAt sums,
                               double * probs, double * s_dscratch, int * s_iscratch)
 {
   const int P = d.nX * d.nY, nA = d.nA;
@@ -125,7 +161,7 @@ __device__ void pair_epilogue(const SweepDev & d, int pair, int q, const int32_t
     const int x = p % d.nX, y = p / d.nX;
     double pm = 0.0;   // Grid<double>::Clear() initial value, M.cpp:727
     for (int a = 0; a < nA; ++a) {
-      int s = sums[(size_t)p * nA + a];
+      int s = sums(p, a);
       double r = pose_response(d, q, s, x, y, a);
       pm = r > pm ? r : pm;
       lbest = r > lbest ? r : lbest;
@@ -142,14 +178,14 @@ __device__ void pair_epilogue(const SweepDev & d, int pair, int q, const int32_t
   for (int p = p0; p < p1; ++p) {
     const int x = p % d.nX, y = p / d.nX;
     for (int a = 0; a < nA; ++a)
-      if (double_equal(pose_response(d, q, sums[(size_t)p * nA + a], x, y, a), best)) ++cnt;
+      if (double_equal(pose_response(d, q, sums(p, a), x, y, a), best)) ++cnt;
   }
   int total = 0;
   int rank = block_exclusive_scan(cnt, s_iscratch, total);
   for (int p = p0; p < p1 && rank < kMaxTies; ++p) {
     const int x = p % d.nX, y = p / d.nX;
     for (int a = 0; a < nA && rank < kMaxTies; ++a)
-      if (double_equal(pose_response(d, q, sums[(size_t)p * nA + a], x, y, a), best)) {
+      if (double_equal(pose_response(d, q, sums(p, a), x, y, a), best)) {
         out.ties[rank++] = p * nA + a;
       }
   }
@@ -157,7 +193,7 @@ __device__ void pair_epilogue(const SweepDev & d, int pair, int q, const int32_t
   __shared__ double s_avg[2];
   if (threadIdx.x == 0) {
     out.best = best;
-    out.best_sum = total > 0 ? sums[out.ties[0]] : 0;
+    out.best_sum = total > 0 ? sums(out.ties[0] / nA, out.ties[0] % nA) : 0;
     out.tie_count = total;
     double ax = 0.0, ay = 0.0;
     const int m = total < kMaxTies ? total : kMaxTies;
@@ -291,7 +327,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_generic(SweepDev d)
     }
     __syncthreads();
     // (4) reduce
-    pair_epilogue(d, pair, q, sums, probs, s_dscratch, s_iscratch);
+    pair_epilogue(d, pair, q, SumsPoseMajor{sums, nA}, probs, s_dscratch, s_iscratch);
   }
 }
 
@@ -349,6 +385,144 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep_fine(SweepDev d, FineDe
 }
 
 
+// ------------------------------------------------------------------------------------------
+// Fast sweep kernel (see FastDev in sm_types.cuh).  One CTA (1024 threads, ~224 KB smem) per pair.
+//   smem: S = one parity sub-grid (bytes, row pitch 304 B) | A = int32 accumulators [a][y][x]
+//   per phase (column parity p, row parity q):
+//     raster the taps of every valid point that fall on (p, q) cells into S          (M.cpp:1080-1104)
+//     warp-item = (angle, x-tile of 16 poses); lane = (row y_l = lane / 4, word j_l = lane % 4),
+//       each thread owns rows y_l + 8 r (r < 6) x 4 consecutive x-poses of its word.
+//     for every FAST beam of (angle, phase, alignment m): ONE 32-bit shared load per row gives the
+//       4 poses' grid bytes; two beams' words are added bytewise first (values <= 100, so 2 fit a
+//       byte), then split into 16-bit fields and accumulated; fields are flushed to A every <= 640
+//       beams.  Integer sums are exact, so the volume equals M.cpp:1190-1201 bit for bit.
+//     SLOW beams (window leaves the grid / wraps a row) take the reference's linear-index rule.
+//   then the same reduction as the generic path (pair_epilogue).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t even_bytes(uint32_t w) { return __byte_perm(w, 0, 0x4240); }   // [b0, 0, b2, 0]
+__device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return __byte_perm(w, 0, 0x4341); }    // [b1, 0, b3, 0]
+
+__global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, FastDev f)
+{
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ double s_dscratch[32];
+  __shared__ int s_iscratch[32];
+  const int sub_words = f.sub_rows * kSubPitchW;
+  uint32_t * S = reinterpret_cast<uint32_t *>(s_raw);
+  uint8_t * S8 = s_raw;
+  int32_t * A = reinterpret_cast<int32_t *>(s_raw + (size_t)sub_words * 4);
+  const int nX = d.nX, nY = d.nY, nA = d.nA, P = nX * nY;
+  const int half = d.ksize / 2, taps = d.ksize * d.ksize;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int y_l = lane >> 2, j_l = lane & 3;
+  constexpr int kPitchB = kSubPitchW * 4;
+
+  for (int pair = blockIdx.x; pair < d.npairs; pair += gridDim.x) {
+    const int q = d.pair_query[pair];
+    const int X0 = f.origin[2 * q], Y0 = f.origin[2 * q + 1];
+    for (int i = threadIdx.x; i < nA * P; i += blockDim.x) A[i] = 0;
+    const int it0 = d.pair_item_start[pair], it1 = d.pair_item_start[pair + 1];
+
+    for (int ph = 0; ph < 4; ++ph) {
+      const int pp = ph & 1, pq = ph >> 1;
+      __syncthreads();
+      for (int i = threadIdx.x; i < sub_words; i += blockDim.x) S[i] = 0;
+      __syncthreads();
+      // ---- raster: taps landing on (pp, pq) cells ----
+      for (int it = it0; it < it1; ++it) {
+        const int32_t * cl = d.cells + (size_t)it * d.max_n;
+        const int total = d.cell_count[it] * taps;
+        for (int t = threadIdx.x; t < total; t += blockDim.x) {
+          const int32_t cell = cl[t / taps];
+          if (cell < 0) continue;
+          const int k = t % taps;
+          const uint32_t kv = d.kern[k];
+          if (kv == 0) continue;
+          const int gx = (cell & 0xFFFF) + d.roi_x + (k % d.ksize) - half;
+          const int gy = (cell >> 16) + d.roi_y + (k / d.ksize) - half;
+          if ((gx & 1) != pp || (gy & 1) != pq) continue;
+          atomic_max_u8(S8 + (gy >> 1) * kPitchB + (gx >> 1), kv);
+        }
+      }
+      __syncthreads();
+      // ---- FAST beams ----
+      for (int wi = warp; wi < nA * f.xtiles; wi += nwarps) {
+        const int a = wi / f.xtiles, xt = wi - a * f.xtiles;
+        const int32_t * cs = f.cls_start + ((size_t)q * nA + a) * 17 + ph * 4;
+        const uint32_t base = (uint32_t)((y_l * kSubPitchW + 4 * xt + j_l) * 4);
+        int32_t * Arow = A + a * P;
+        for (int m = 0; m < 4; ++m) {
+          int b = cs[m];
+          const int e = cs[m + 1];
+          const int x0 = 4 * (4 * xt + j_l) - m;
+          while (b < e) {
+            const int ce = min(e, b + kFastChunk);
+            uint32_t T0[kFastRowTiles], T1[kFastRowTiles];
+#pragma unroll
+            for (int r = 0; r < kFastRowTiles; ++r) { T0[r] = 0; T1[r] = 0; }
+            for (; b + 1 < ce; b += 2) {
+              const uint32_t o0 = base + 4u * f.beams[b], o1 = base + 4u * f.beams[b + 1];
+#pragma unroll
+              for (int r = 0; r < kFastRowTiles; ++r) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * kPitchB) +
+                                   *reinterpret_cast<const uint32_t *>(S8 + o1 + r * 8 * kPitchB);
+                T0[r] += even_bytes(w);
+                T1[r] += odd_bytes(w);
+              }
+            }
+            if (b < ce) {
+              const uint32_t o0 = base + 4u * f.beams[b];
+#pragma unroll
+              for (int r = 0; r < kFastRowTiles; ++r) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * kPitchB);
+                T0[r] += even_bytes(w);
+                T1[r] += odd_bytes(w);
+              }
+              ++b;
+            }
+            // flush the 16-bit fields: pose x = x0 + t, t = 0..3
+#pragma unroll
+            for (int r = 0; r < kFastRowTiles; ++r) {
+              const int y = y_l + 8 * r;
+              if (y >= nY) continue;
+              int32_t * dst = Arow + y * nX + x0;
+              const int v0 = T0[r] & 0xFFFF, v1 = T1[r] & 0xFFFF, v2 = T0[r] >> 16, v3 = T1[r] >> 16;
+              if (v0 && (unsigned)(x0 + 0) < (unsigned)nX) atomicAdd(dst + 0, v0);
+              if (v1 && (unsigned)(x0 + 1) < (unsigned)nX) atomicAdd(dst + 1, v1);
+              if (v2 && (unsigned)(x0 + 2) < (unsigned)nX) atomicAdd(dst + 2, v2);
+              if (v3 && (unsigned)(x0 + 3) < (unsigned)nX) atomicAdd(dst + 3, v3);
+            }
+          }
+        }
+      }
+      // ---- SLOW beams: the reference's rule on the linear index (M.cpp:1192-1200), this phase's cells only ----
+      {
+        const int32_t * ss = f.slow_start + (size_t)q * (nA + 1);
+        const int nslow = ss[nA] - ss[0];
+        if (nslow > 0) {
+          const int32_t * pos = d.posidx + (size_t)q * P;
+          for (int a = 0; a < nA; ++a) {
+            const int sb = ss[a], se = ss[a + 1];
+            const int work = (se - sb) * P;
+            for (int t = threadIdx.x; t < work; t += blockDim.x) {
+              const int bi = t / P, p = t - bi * P;
+              const int idx = pos[p] + f.slow[sb + bi];
+              if ((unsigned)idx >= (unsigned)d.data_size) continue;
+              const int row = idx / d.stride, col = idx - row * d.stride;
+              if ((col & 1) != pp || (row & 1) != pq) continue;
+              const int v = S8[(row >> 1) * kPitchB + (col >> 1)];
+              if (v) atomicAdd(A + a * P + p, v);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // S is free now: reuse it as the FP64 scratch of the reduction (5 P doubles)
+    pair_epilogue(d, pair, q, SumsAngleMajor{A, P}, reinterpret_cast<double *>(s_raw), s_dscratch, s_iscratch);
+  }
+}
+
 // Per-query best-response key for the multi-GPU sweep: key = best_sum << 32 | (0xFFFFFFFF - global
 // candidate id), so that a max-reduction (here atomicMax, across GPUs ncclMax) picks the highest
 // integer correlation sum and breaks ties towards the lowest candidate id, deterministically.
@@ -403,6 +577,8 @@ static void coarse_search(const b200sm * h, double off[2], double res[2])
   off[0] = off[1] = 0.5 * (dim - 1) * r;   // M.cpp:579-581
   res[0] = res[1] = 2 * r;                 // M.cpp:584-585
 }
+
+static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st);
 
 static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b200_scan * scans, int nscans,
                         const int32_t * chain_start, int nchains, const int32_t * pair_query,
@@ -593,8 +769,90 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   d.out = S.d_out.p;
   if (!S.ev0) { B200_CUDA(cudaEventCreate(&S.ev0)); B200_CUDA(cudaEventCreate(&S.ev1)); }
   B200_CUDA(cudaStreamSynchronize(st));
+  build_fast_tables(h, S, st);
   S.uploaded = true;
   return B200_OK;
+}
+
+// Builds the per-query beam lists of the fast path; returns false when this sweep cannot use it.
+static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
+{
+  const GridGeom & g = h->g;
+  const CorrPlan & p0 = S.plans[0];
+  const int nX = p0.nX, nY = p0.nY, nA = p0.nA, n = p0.n, nq = S.nq;
+  S.fast.enabled = 0;
+  if (g.order_dependent) return false;
+  if (nY > 8 * kFastRowTiles || (g.stride & 1)) return false;
+  if (g.stride / 2 > kSubPitchW * 4 - 16) return false;   // sub-grid row + the 3-word overhang must fit the pitch
+  const int xtiles = (nX + 3 + 15) / 16;
+  const int sub_rows = (g.height + 1) / 2 + 8;               // + padding rows read by idle row tiles
+  const size_t smem = (size_t)sub_rows * kSubPitchW * 4 + (size_t)nA * nX * nY * 4;
+  if (smem > 227 * 1024 - 1024) return false;
+  if ((size_t)5 * nX * nY * sizeof(double) > (size_t)sub_rows * kSubPitchW * 4) return false;   // epilogue scratch reuses S
+  std::vector<int32_t> origin(2 * (size_t)nq), cls_start((size_t)nq * nA * 17), slow, slow_start((size_t)nq * (nA + 1));
+  std::vector<uint16_t> beams;
+  beams.reserve((size_t)nq * nA * n);
+  for (int q = 0; q < nq; ++q) {
+    const CorrPlan & pl = S.plans[q];
+    for (int k = 1; k < nX; ++k) if (pl.xs[k] != pl.xs[0] + 2 * k) return false;   // coarse step must be exactly 2 cells
+    for (int k = 1; k < nY; ++k) if (pl.ys[k] != pl.ys[0] + 2 * k) return false;
+    const int X0 = pl.xs[0], Y0 = pl.ys[0];
+    origin[2 * q] = X0; origin[2 * q + 1] = Y0;
+    std::vector<uint16_t> group[16];
+    for (int a = 0; a < nA; ++a) {
+      for (auto & v : group) v.clear();
+      slow_start[(size_t)q * (nA + 1) + a] = (int32_t)slow.size();
+      for (int i = 0; i < n; ++i) {
+        const int32_t off = pl.offsets[(size_t)a * n + i];
+        if (off == kInvalidScan) continue;
+        const int gx = pl.ogx[(size_t)a * n + i], gy = pl.ogy[(size_t)a * n + i];
+        const int Xb = X0 + gx, Yb = Y0 + gy;
+        const bool inside = Xb >= 0 && Xb + 2 * (nX - 1) < g.stride && Yb >= 0 && Yb + 2 * (nY - 1) < g.height;
+        if (inside) {
+          const int pp = Xb & 1, pq = Yb & 1, c = Xb >> 1, r = Yb >> 1;
+          const int wo = r * kSubPitchW + (c >> 2);
+          group[(pq * 2 + pp) * 4 + (c & 3)].push_back((uint16_t)wo);
+        } else {
+          const int32_t dv = device_offset(off, g.data_size);
+          if (dv != kDevInvalid) slow.push_back(dv);   // can still index [0, data_size) for some pose
+        }
+      }
+      int32_t * cs = &cls_start[((size_t)q * nA + a) * 17];
+      for (int k = 0; k < 16; ++k) {
+        cs[k] = (int32_t)beams.size();
+        std::sort(group[k].begin(), group[k].end());
+        beams.insert(beams.end(), group[k].begin(), group[k].end());
+      }
+      cs[16] = (int32_t)beams.size();
+    }
+    slow_start[(size_t)q * (nA + 1) + nA] = (int32_t)slow.size();
+  }
+  // slow_start must be relative to one array: it is (single vector `slow`)
+  h2d(S.d_fast_origin, origin.data(), origin.size(), st);
+  h2d(S.d_fast_cls, cls_start.data(), cls_start.size(), st);
+  S.d_fast_beams.reserve(std::max<size_t>(beams.size(), 1) + 8);
+  if (!beams.empty()) B200_CUDA(cudaMemcpyAsync(S.d_fast_beams.p, beams.data(), beams.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  S.h2d_bytes += (int64_t)(beams.size() * sizeof(uint16_t));
+  slow.push_back(0);
+  h2d(S.d_fast_slow, slow.data(), slow.size(), st);
+  h2d(S.d_fast_slow_start, slow_start.data(), slow_start.size(), st);
+  B200_CUDA(cudaStreamSynchronize(st));   // the vectors above go out of scope
+  S.fast.enabled = 1;
+  S.fast.sub_rows = sub_rows;
+  S.fast.xtiles = xtiles;
+  S.fast.origin = S.d_fast_origin.p;
+  S.fast.beams = S.d_fast_beams.p;
+  S.fast.cls_start = S.d_fast_cls.p;
+  S.fast.slow = S.d_fast_slow.p;
+  S.fast.slow_start = S.d_fast_slow_start.p;
+  S.fast_smem = smem;
+  {
+    int dev = 0, sms = 148;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    S.fast_blocks = std::min(S.npairs, sms);
+  }
+  return true;
 }
 
 static int sweep_run(b200sm * h)
@@ -604,14 +862,19 @@ static int sweep_run(b200sm * h)
   cudaStream_t st = h->stream;
   const SweepDev & d = S.dev;
   if (S.nitems > 0) {
-    k_find_valid<<<(S.nitems + 63) / 64, 64, 0, st>>>(d);
+    k_find_valid<<<(S.nitems + kFvWarps - 1) / kFvWarps, kFvWarps * 32, (size_t)kFvWarps * S.max_n, st>>>(d);
     B200_CUDA(cudaGetLastError());
     h->launches++;
   }
-  const size_t smem = (size_t)d.nA * d.n * sizeof(int32_t);
-  B200_CUDA(cudaFuncSetAttribute(k_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B200_CUDA(cudaEventRecord(S.ev0, st));
-  k_sweep_generic<<<S.blocks, kSweepThreads, smem, st>>>(d);
+  if (S.fast.enabled && !h->force_generic) {
+    B200_CUDA(cudaFuncSetAttribute(k_sweep_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.fast_smem));
+    k_sweep_fast<<<S.fast_blocks, kFastThreads, S.fast_smem, st>>>(d, S.fast);
+  } else {
+    const size_t smem = (size_t)d.nA * d.n * sizeof(int32_t);
+    B200_CUDA(cudaFuncSetAttribute(k_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sweep_generic<<<S.blocks, kSweepThreads, smem, st>>>(d);
+  }
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaEventRecord(S.ev1, st));
   h->launches++;

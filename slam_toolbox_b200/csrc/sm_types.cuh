@@ -31,6 +31,7 @@ struct CorrPlan {
   int nX = 0, nY = 0, nA = 0, n = 0;
   double center[3] = {0, 0, 0}, sp_off[2] = {0, 0}, sp_res[2] = {0, 0}, ang_off = 0, ang_res = 0;
   std::vector<int32_t> offsets;            // nA x n, reference linear offsets (INVALID_SCAN kept)
+  std::vector<int32_t> ogx, ogy;           // nA x n, the grid-cell offsets the linear offsets were built from
   std::vector<int32_t> xs, ys;             // grid column / row (ROI included) per x / y index
   std::vector<int32_t> px, py;             // search-space-probability grid cell per x / y index
   std::vector<double> xrel, yrel;          // m_xPoses / m_yPoses
@@ -105,6 +106,27 @@ struct SweepDev {
   PairOut * out;
 };
 
+// Fast sweep path (k_sweep_fast): per-query beam lists in "parity sub-grid" form.
+//   The coarse search steps 2 cells in x and y, so one beam only ever reads grid cells of ONE
+//   (column parity, row parity) class: the grid is kept in shared memory as one parity sub-grid
+//   at a time (4 phases), in which consecutive x-poses are consecutive BYTES -> one 32-bit shared
+//   load serves 4 poses.  Beams are grouped by (angle, phase, column alignment m = sub-column & 3);
+//   a FAST beam (whole 41x41 window inside the grid) is a 16-bit word offset into the sub-grid.
+constexpr int kFastThreads = 1024;
+constexpr int kSubPitchW = 76;      // words per sub-grid row: 8 rows x 4 words per warp hit 32 distinct banks
+constexpr int kFastRowTiles = 6;    // rows per thread (y_l + 8 r), nY <= 48
+constexpr int kFastChunk = 640;     // beams accumulated in 16-bit fields before a flush (640 * 100 < 65536)
+struct FastDev {
+  int enabled;
+  int sub_rows;                  // allocated sub-grid rows (incl. padding rows)
+  int xtiles;                    // ceil((nX + 3) / 16)
+  const int32_t * origin;        // [nq][2]  grid column / row of pose (0, 0)
+  const uint16_t * beams;        // FAST descriptors, grouped
+  const int32_t * cls_start;     // [nq][nA][17] group boundaries into beams (group = phase * 4 + m)
+  const int32_t * slow;          // SLOW beams: device-form linear offsets
+  const int32_t * slow_start;    // [nq][nA + 1]
+};
+
 struct FineDev {
   int P, nA;
   const int32_t * offsets;   // [npairs][nA][n]
@@ -126,6 +148,11 @@ struct SweepHost {
     d_cells, d_cell_count, d_ws_sums, d_fine_off, d_fine_pos, d_fine_sums;
   DevBuf<double> d_qgeom, d_center, d_qd, d_angpen, d_points, d_ws_probs;
   DevBuf<uint8_t> d_ws_grid, d_kernel;
+  DevBuf<uint16_t> d_fast_beams;
+  DevBuf<int32_t> d_fast_origin, d_fast_cls, d_fast_slow, d_fast_slow_start;
+  FastDev fast{};
+  size_t fast_smem = 0;
+  int fast_blocks = 0;
   DevBuf<PairOut> d_out;
   PinBuf<PairOut> h_out;
   PinBuf<int32_t> h_i;
@@ -152,6 +179,7 @@ struct b200sm {
   b200::DevBuf<int32_t> d_cells, d_offsets, d_sums;
   b200::PinBuf<int32_t> h_stage_i, h_sums;
   bool have_raster = false;
+  bool force_generic = false;   // testing: run sweeps on the generic kernel even when the fast path applies
 
   b200::SweepHost sweep;
 

@@ -160,3 +160,26 @@ def test_full_size_sweep_properties():
     for j in (0, 17, 500, 999, int(np.argmax(r1))):
         e = pm.match(pq, H.port_scans(sw.cand_ranges[j], sw.cand_poses[j]), False, False)
         assert e[0] == r1[j] and np.array_equal(e[1], m1[j]) and np.array_equal(e[2], c1[j])
+
+
+@pytest.mark.parametrize("grid", [H.GRID_LOOP, (4.0, 0.05, 0.03, 6.0), (2.0, 0.05, 0.05, 8.0)])
+def test_fast_and_generic_sweep_kernels_agree_with_the_oracle(grid):
+    """The shared-memory fast path (parity sub-grids, word loads) against the generic kernel and the oracle.
+    A short range threshold puts many beam windows partly / wholly outside the grid, which exercises the
+    SLOW-beam rule (linear-index wrap, Mapper.cpp:1192-1197) next to the FAST lists."""
+    sw = synth.make_loop_sweep(31, n_queries=2, n_chains=10, chain_len=2, inf_frac=0.02)
+    pm, gm = H.port_matcher(H.MAPPER_LOOP, grid), H.gpu_matcher(H.MAPPER_LOOP, grid)
+    pc, pq = H.port_scans(sw.cand_ranges, sw.cand_poses), H.port_scans(sw.query_ranges, sw.query_poses)
+    gc, gq = H.gpu_block(sw.cand_ranges, sw.cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
+    exp = [pm.match(pq[q], pc[sw.chain_start[c]:sw.chain_start[c + 1]], False, False) for q in range(2) for c in range(10)]
+    fast = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
+    fast_best = gm.batch_best()
+    gm.set_option("force_generic_sweep", 1)
+    gen = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
+    gen_best = gm.batch_best()
+    for a, b in zip(fast, gen):
+        assert np.array_equal(a, b)
+    for a, b in zip(fast_best, gen_best):
+        assert np.array_equal(a, b)
+    assert np.array_equal(fast[0], np.array([e[0] for e in exp]))
+    assert np.array_equal(fast[1], np.array([e[1] for e in exp])) and np.array_equal(fast[2], np.array([e[2] for e in exp]))

@@ -460,26 +460,45 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
             uint32_t T0[kFastRowTiles], T1[kFastRowTiles];
 #pragma unroll
             for (int r = 0; r < kFastRowTiles; ++r) { T0[r] = 0; T1[r] = 0; }
-            for (; b + 1 < ce; b += 2) {
-              const uint32_t o0 = base + 4u * f.beams[b], o1 = base + 4u * f.beams[b + 1];
+            // descriptors are fetched 32 at a time (one per lane, coalesced) and broadcast by shuffle
+            for (int b0 = b; b0 < ce; b0 += 32) {
+              const int cnt = min(32, ce - b0);
+              const uint32_t mine = (lane < cnt) ? 4u * f.beams[b0 + lane] : 0u;
+              int k = 0;
+              for (; k + 3 < cnt; k += 4) {   // 4 beams: two byte-wise pair sums, one 3-input add per field
+                const uint32_t o0 = base + __shfl_sync(0xffffffffu, mine, k), o1 = base + __shfl_sync(0xffffffffu, mine, k + 1);
+                const uint32_t o2 = base + __shfl_sync(0xffffffffu, mine, k + 2), o3 = base + __shfl_sync(0xffffffffu, mine, k + 3);
 #pragma unroll
-              for (int r = 0; r < kFastRowTiles; ++r) {
-                const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * kPitchB) +
-                                   *reinterpret_cast<const uint32_t *>(S8 + o1 + r * 8 * kPitchB);
-                T0[r] += even_bytes(w);
-                T1[r] += odd_bytes(w);
+                for (int r = 0; r < kFastRowTiles; ++r) {
+                  const uint32_t wa = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * kPitchB) +
+                                      *reinterpret_cast<const uint32_t *>(S8 + o1 + r * 8 * kPitchB);
+                  const uint32_t wb = *reinterpret_cast<const uint32_t *>(S8 + o2 + r * 8 * kPitchB) +
+                                      *reinterpret_cast<const uint32_t *>(S8 + o3 + r * 8 * kPitchB);
+                  T0[r] = T0[r] + even_bytes(wa) + even_bytes(wb);
+                  T1[r] = T1[r] + odd_bytes(wa) + odd_bytes(wb);
+                }
+              }
+              for (; k + 1 < cnt; k += 2) {
+                const uint32_t o0 = base + __shfl_sync(0xffffffffu, mine, k), o1 = base + __shfl_sync(0xffffffffu, mine, k + 1);
+#pragma unroll
+                for (int r = 0; r < kFastRowTiles; ++r) {
+                  const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * kPitchB) +
+                                     *reinterpret_cast<const uint32_t *>(S8 + o1 + r * 8 * kPitchB);
+                  T0[r] += even_bytes(w);
+                  T1[r] += odd_bytes(w);
+                }
+              }
+              if (k < cnt) {
+                const uint32_t o0 = base + __shfl_sync(0xffffffffu, mine, k);
+#pragma unroll
+                for (int r = 0; r < kFastRowTiles; ++r) {
+                  const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * kPitchB);
+                  T0[r] += even_bytes(w);
+                  T1[r] += odd_bytes(w);
+                }
               }
             }
-            if (b < ce) {
-              const uint32_t o0 = base + 4u * f.beams[b];
-#pragma unroll
-              for (int r = 0; r < kFastRowTiles; ++r) {
-                const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * kPitchB);
-                T0[r] += even_bytes(w);
-                T1[r] += odd_bytes(w);
-              }
-              ++b;
-            }
+            b = ce;
             // flush the 16-bit fields: pose x = x0 + t, t = 0..3
 #pragma unroll
             for (int r = 0; r < kFastRowTiles; ++r) {

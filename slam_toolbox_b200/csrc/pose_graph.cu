@@ -22,8 +22,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -379,6 +381,630 @@ __global__ void __launch_bounds__(kPgThreads) k_pg_pcg(PgDev d, double inv_radiu
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_pg_pcg_smem: the same PCG, restructured for graphs whose per-CTA share fits shared memory
+// (cfg4: 68 nodes / ~550 off-diagonal blocks per CTA).  Each CTA owns a contiguous range of nodes and
+// keeps THEIR rows of the block-sparse normal matrix (3x3 blocks, already oriented), the diagonal
+// blocks, the preconditioner and all CG vectors of its nodes in shared memory for the whole solve.
+// Per CG iteration the only global traffic is the neighbour gather of z and p (L2) and 2 light
+// grid barriers (one atomic counter; partial dot products are summed by every CTA in the same fixed
+// order, so the result is bit-reproducible).
+// ------------------------------------------------------------------------------------------
+struct PcgSmemCfg {
+  int npc;          // nodes per CTA
+  int max_slots;    // max off-diagonal blocks of one CTA
+  double * gz;      // [N][3]
+  double * gp;      // [2][N][3]
+  unsigned int * bar;   // barrier counter (zeroed before launch)
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int * bar, unsigned int target)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double ld_cg(const double * p) { return __ldcg(p); }
+
+__global__ void __launch_bounds__(512, 1) k_pg_pcg_smem(PgDev d, PcgSmemCfg c, double inv_radius, double tol, int max_iter)
+{
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  __shared__ double red[4 * 32];
+  __shared__ double bc[1];
+  const int T = blockDim.x, tid = threadIdx.x, G = gridDim.x;
+  const int lo = min(d.N, (int)blockIdx.x * c.npc), hi = min(d.N, lo + c.npc), nloc = hi - lo;
+  const int s_lo = d.adj_start[lo], nslots = d.adj_start[hi] - s_lo;
+  double * sB = reinterpret_cast<double *>(sm_raw);            // [max_slots][9]
+  double * sV = sB + (size_t)c.max_slots * 9;                  // [max_slots][3]
+  double * sH = sV + (size_t)c.max_slots * 3;                  // [npc][6]
+  double * sMi = sH + (size_t)c.npc * 6;                       // [npc][6]
+  double * sR = sMi + (size_t)c.npc * 6;                       // [npc][3] each below
+  double * sZ = sR + (size_t)c.npc * 3;
+  double * sP = sZ + (size_t)c.npc * 3;
+  double * sQ = sP + (size_t)c.npc * 3;
+  double * sY = sQ + (size_t)c.npc * 3;
+  int * sCol = reinterpret_cast<int *>(sY + (size_t)c.npc * 3);   // [max_slots]
+  int * sStart = sCol + c.max_slots;                              // [npc + 1]
+  unsigned int bar_target = 0;
+
+  // ---- prologue: load this CTA's rows ----
+  for (int i = tid; i <= nloc; i += T) sStart[i] = d.adj_start[lo + i] - s_lo;
+  for (int s = tid; s < nslots; s += T) {
+    const int a = d.adj[s_lo + s];
+    const int e = a >> 1, side = a & 1;
+    const double * M = d.lin + (size_t)kLin * e + 21;
+    sCol[s] = d.eidx[2 * e + (side ? 0 : 1)];
+    double * B = sB + 9 * s;
+    if (side == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) B[k] = M[k];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) B[3 * i + j] = M[3 * j + i];
+    }
+  }
+  double acc[2] = {0, 0};
+  for (int n = tid; n < nloc; n += T) {
+    const int i = lo + n;
+    const double * h = d.Hd + 6 * i, * dg = d.diag + 3 * i;
+    const double a00 = h[0] + dg[0] * inv_radius, a01 = h[1], a02 = h[2], a11 = h[3] + dg[1] * inv_radius, a12 = h[4],
+                 a22 = h[5] + dg[2] * inv_radius;
+    double * H = sH + 6 * n;
+    H[0] = a00; H[1] = a01; H[2] = a02; H[3] = a11; H[4] = a12; H[5] = a22;
+    const double c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+    const double c11 = a00 * a22 - a02 * a02, c12 = a01 * a02 - a00 * a12, c22 = a00 * a11 - a01 * a01;
+    const double id = 1.0 / (a00 * c00 + a01 * c01 + a02 * c02);
+    double * mi = sMi + 6 * n;
+    mi[0] = c00 * id; mi[1] = c01 * id; mi[2] = c02 * id; mi[3] = c11 * id; mi[4] = c12 * id; mi[5] = c22 * id;
+    const double b0 = d.g[3 * i], b1 = d.g[3 * i + 1], b2 = d.g[3 * i + 2];
+    const double z0 = mi[0] * b0 + mi[1] * b1 + mi[2] * b2, z1 = mi[1] * b0 + mi[3] * b1 + mi[4] * b2,
+                 z2 = mi[2] * b0 + mi[4] * b1 + mi[5] * b2;
+    sR[3 * n] = b0; sR[3 * n + 1] = b1; sR[3 * n + 2] = b2;
+    sZ[3 * n] = z0; sZ[3 * n + 1] = z1; sZ[3 * n + 2] = z2;
+    sP[3 * n] = 0; sP[3 * n + 1] = 0; sP[3 * n + 2] = 0;
+    sY[3 * n] = 0; sY[3 * n + 1] = 0; sY[3 * n + 2] = 0;
+    c.gz[3 * i] = z0; c.gz[3 * i + 1] = z1; c.gz[3 * i + 2] = z2;
+    c.gp[3 * i] = 0; c.gp[3 * i + 1] = 0; c.gp[3 * i + 2] = 0;
+    acc[0] += b0 * b0 + b1 * b1 + b2 * b2;
+    acc[1] += b0 * z0 + b1 * z1 + b2 * z2;
+  }
+  block_sum<2>(acc, red);
+  if (tid == 0) { d.partial[blockIdx.x] = acc[0]; d.partial[kMaxPartials + blockIdx.x] = acc[1]; }
+  bar_target += G;
+  grid_barrier(c.bar, bar_target);
+  const double bb = grid_total(d, 0, G, bc);
+  double rz = grid_total(d, 1, G, bc);
+  double rr = bb;
+  const double stop = tol * tol * bb;
+  int it = 0;
+  double beta = 0.0;
+  int cur = 0;   // gp[cur] holds p_old
+  if (bb > 0.0) {
+    while (it < max_iter) {
+      const double * gpo = c.gp + (size_t)cur * 3 * d.N;
+      double * gpn = c.gp + (size_t)(cur ^ 1) * 3 * d.N;
+      // ---- phase A: gather v_j = z_j + beta p_j ; p_new ; q = A p_new ; partial p.q ----
+      for (int s = tid; s < nslots; s += T) {
+        const int j = sCol[s];
+        double v0, v1, v2;
+        if (j >= lo && j < hi) {   // neighbour owned by this CTA: shared memory
+          const int n = j - lo;
+          v0 = sZ[3 * n] + beta * sP[3 * n]; v1 = sZ[3 * n + 1] + beta * sP[3 * n + 1]; v2 = sZ[3 * n + 2] + beta * sP[3 * n + 2];
+        } else {
+          v0 = ld_cg(c.gz + 3 * j) + beta * ld_cg(gpo + 3 * j);
+          v1 = ld_cg(c.gz + 3 * j + 1) + beta * ld_cg(gpo + 3 * j + 1);
+          v2 = ld_cg(c.gz + 3 * j + 2) + beta * ld_cg(gpo + 3 * j + 2);
+        }
+        sV[3 * s] = v0; sV[3 * s + 1] = v1; sV[3 * s + 2] = v2;
+      }
+      __syncthreads();
+      for (int k = tid; k < 3 * nloc; k += T) {   // new search direction of own nodes (after the local reads above)
+        const double pn = sZ[k] + beta * sP[k];
+        sQ[k] = pn;   // temporarily: p_new
+      }
+      __syncthreads();
+      for (int k = tid; k < 3 * nloc; k += T) { sP[k] = sQ[k]; gpn[3 * lo + k] = sQ[k]; }
+      __syncthreads();
+      double a1[1] = {0};
+      for (int k = tid; k < 3 * nloc; k += T) {
+        const int n = k / 3, r = k - 3 * n;
+        const double * H = sH + 6 * n;
+        const double p0 = sP[3 * n], p1 = sP[3 * n + 1], p2 = sP[3 * n + 2];
+        double q;
+        if (r == 0) q = H[0] * p0 + H[1] * p1 + H[2] * p2;
+        else if (r == 1) q = H[1] * p0 + H[3] * p1 + H[4] * p2;
+        else q = H[2] * p0 + H[4] * p1 + H[5] * p2;
+        for (int s = sStart[n]; s < sStart[n + 1]; ++s) {
+          const double * B = sB + 9 * s + 3 * r, * v = sV + 3 * s;
+          q += B[0] * v[0] + B[1] * v[1] + B[2] * v[2];
+        }
+        sQ[k] = q;
+        a1[0] += sP[k] * q;
+      }
+      block_sum<1>(a1, red);
+      if (tid == 0) d.partial[2 * kMaxPartials + blockIdx.x] = a1[0];
+      bar_target += G;
+      grid_barrier(c.bar, bar_target);
+      const double pq = grid_total(d, 2, G, bc);
+      const double alpha = rz / pq;
+      // ---- phase B: y += alpha p ; r -= alpha q ; z = Minv r ; partials r.z, r.r ----
+      for (int k = tid; k < 3 * nloc; k += T) { sY[k] += alpha * sP[k]; sR[k] -= alpha * sQ[k]; }
+      __syncthreads();
+      double a2[2] = {0, 0};
+      for (int k = tid; k < 3 * nloc; k += T) {
+        const int n = k / 3, r = k - 3 * n;
+        const double * mi = sMi + 6 * n;
+        const double r0 = sR[3 * n], r1 = sR[3 * n + 1], r2 = sR[3 * n + 2];
+        double z;
+        if (r == 0) z = mi[0] * r0 + mi[1] * r1 + mi[2] * r2;
+        else if (r == 1) z = mi[1] * r0 + mi[3] * r1 + mi[4] * r2;
+        else z = mi[2] * r0 + mi[4] * r1 + mi[5] * r2;
+        sZ[k] = z;
+        c.gz[3 * lo + k] = z;
+        a2[0] += sR[k] * z;
+        a2[1] += sR[k] * sR[k];
+      }
+      block_sum<2>(a2, red);
+      const int s0 = 3 + 2 * (it & 1);
+      if (tid == 0) { d.partial[s0 * kMaxPartials + blockIdx.x] = a2[0]; d.partial[(s0 + 1) * kMaxPartials + blockIdx.x] = a2[1]; }
+      bar_target += G;
+      grid_barrier(c.bar, bar_target);
+      const double rz_new = grid_total(d, s0, G, bc);
+      rr = grid_total(d, s0 + 1, G, bc);
+      ++it;
+      cur ^= 1;
+      if (!(rr > stop) || !(pq > 0.0)) break;
+      beta = rz_new / rz;
+      rz = rz_new;
+    }
+  }
+  for (int k = tid; k < 3 * nloc; k += T) d.y[3 * lo + k] = sY[k];
+  if (blockIdx.x == 0 && tid == 0) {
+    d.scalars[8] = (double)it;
+    d.scalars[9] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_pg_pcg_2lvl: shared-memory-resident PCG (as k_pg_pcg_smem) with a TWO-LEVEL preconditioner
+//     M^-1 = blockdiag(H_ii + D_i)^-1  +  P Ac^-1 P^T ,   Ac = P^T (H + D) P
+// One aggregate per CTA (its contiguous node range); P holds the aggregate's three rigid-body modes
+// (translation x, y, rotation about the aggregate's centroid) expressed in the Jacobi-scaled
+// variables.  The low-frequency deformation modes that make block-Jacobi CG need thousands of
+// iterations on a pose graph are removed by the coarse solve (measured: ~4.6x fewer iterations).
+//   setup per solve: every CTA builds its 3 rows of Ac, then a block Gauss-Jordan over the grid
+//     (one 3-row pivot exchange per aggregate) leaves each CTA holding ITS 3 rows of Ac^-1 in smem;
+//   per CG iteration: 2 flag-based exchanges (no atomic barrier): {p.q, P^T q} and {r.z, r.r};
+//     the coarse residual P^T r is carried by the recurrence rc -= alpha P^T q, identically in
+//     every CTA, so the coarse correction needs no extra exchange.
+// All reductions are summed in a fixed order: results are bit-reproducible.
+// ------------------------------------------------------------------------------------------
+struct Pcg2Cfg {
+  int npc, max_slots;
+  double * gz;            // [N][3]
+  double * gp;            // [2][N][3]
+  double * gPt;           // [N][9]   P~ block of every node (rows: node comps, cols: coarse comps)
+  double * gRow;          // [G][3][2 nc] published pivot rows of the block Gauss-Jordan
+  double * grc;           // [G][3]   initial coarse residual
+  double * e1;            // [2][G][4]  {p.q partial, P^T q (3)}
+  double * e2;            // [2][G][2]  {r.z partial, r.r partial}
+  unsigned int * gjflag;  // [G]
+  unsigned int * bar;     // atomic barrier counter (set-up only)
+};
+
+__device__ __forceinline__ double pg_sentinel() { return __longlong_as_double(0x7FF8DEADBEEF0001LL); }
+__device__ __forceinline__ bool pg_is_sentinel(double v) { return __double_as_longlong(v) == 0x7FF8DEADBEEF0001LL; }
+__device__ __forceinline__ double ld_volatile(const double * p)
+{
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Exchange slots: one 256-byte line per (parity, CTA) so that the all-to-all polling spreads over
+// every L2 slice instead of hammering a few sectors; a slot holds K <= 4 doubles, each self-flagged
+// (a value is "published" when it is not the sentinel).  One thread per source CTA polls with
+// 16-byte loads.
+constexpr int kSlotStride = 32;   // doubles
+__device__ __forceinline__ void ld_volatile2(const double * p, double & a, double & b)
+{
+  asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p) : "memory");
+}
+template <int K>
+__device__ __forceinline__ void poll_slots(const double * slots, int G, double * s_out)
+{
+  for (int t = threadIdx.x; t < G; t += blockDim.x) {
+    const double * p = slots + (size_t)t * kSlotStride;
+    double v[4];
+    bool ok;
+    do {
+      ld_volatile2(p, v[0], v[1]);
+      if (K > 2) ld_volatile2(p + 2, v[2], v[3]);
+      ok = true;
+#pragma unroll
+      for (int k = 0; k < K; ++k) ok = ok && !pg_is_sentinel(v[k]);
+    } while (!ok);
+#pragma unroll
+    for (int k = 0; k < K; ++k) s_out[t * K + k] = v[k];
+    __threadfence();
+  }
+  __syncthreads();
+}
+// fixed-order sum of s[i * stride + off], i < n, by warp 0; broadcast through bc
+__device__ __forceinline__ double ordered_sum(const double * s, int n, int stride, int off, double * bc)
+{
+  if (threadIdx.x < 32) {
+    double a = 0;
+    for (int i = threadIdx.x; i < n; i += 32) a += s[i * stride + off];
+    a = warp_sum(a);
+    if (threadIdx.x == 0) bc[0] = a;
+  }
+  __syncthreads();
+  const double r = bc[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, double inv_radius, double tol, int max_iter)
+{
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  __shared__ double red[4 * 32];
+  __shared__ double bc[1];
+  __shared__ double s_small[16];
+  const int T = blockDim.x, tid = threadIdx.x, G = gridDim.x, I = blockIdx.x;
+  const int nc = 3 * G;
+  const int lo = min(d.N, I * c.npc), hi = min(d.N, lo + c.npc), nloc = hi - lo;
+  const int s_lo = d.adj_start[lo], nslots = d.adj_start[hi] - s_lo;
+  double * sB = reinterpret_cast<double *>(sm_raw);            // [max_slots][9]
+  double * sV = sB + (size_t)c.max_slots * 9;                  // [max_slots][3]
+  double * sH = sV + (size_t)c.max_slots * 3;                  // [npc][6]
+  double * sMi = sH + (size_t)c.npc * 6;                       // [npc][6]
+  double * sR = sMi + (size_t)c.npc * 6;                       // [npc][3] each below
+  double * sZ = sR + (size_t)c.npc * 3;
+  double * sP = sZ + (size_t)c.npc * 3;
+  double * sQ = sP + (size_t)c.npc * 3;
+  double * sY = sQ + (size_t)c.npc * 3;
+  double * sPt = sY + (size_t)c.npc * 3;                       // [npc][9]
+  double * sAc = sPt + (size_t)c.npc * 9;                      // [3][2 nc] -> right half becomes rows of Ac^-1
+  double * sRc = sAc + (size_t)6 * nc;                         // [nc] coarse residual (identical in all CTAs)
+  double * sEx = sRc + nc;                                     // [4 G] exchange scratch
+  int * sCol = reinterpret_cast<int *>(sEx + (size_t)4 * G);   // [max_slots]
+  int * sNode = sCol + c.max_slots;                            // [max_slots] local node of the slot
+  int * sStart = sNode + c.max_slots;                          // [npc + 1]
+  unsigned int bar_target = 0;
+  const double SENT = pg_sentinel();
+  unsigned long long t_start = 0, t_setup = 0, t_gj = 0;
+  if (I == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+
+  // ---- load this CTA's rows (as k_pg_pcg_smem) ----
+  for (int i = tid; i <= nloc; i += T) sStart[i] = d.adj_start[lo + i] - s_lo;
+  __syncthreads();
+  for (int n = tid; n < nloc; n += T)
+    for (int s = sStart[n]; s < sStart[n + 1]; ++s) sNode[s] = n;
+  for (int s = tid; s < nslots; s += T) {
+    const int a = d.adj[s_lo + s];
+    const int e = a >> 1, side = a & 1;
+    const double * M = d.lin + (size_t)kLin * e + 21;
+    sCol[s] = d.eidx[2 * e + (side ? 0 : 1)];
+    double * B = sB + 9 * s;
+    if (side == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) B[k] = M[k];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) B[3 * i + j] = M[3 * j + i];
+    }
+  }
+  // centroid of the aggregate's free nodes (fixed-order sum by thread 0: nloc is small)
+  if (tid == 0) {
+    double cx = 0, cy = 0; int cnt = 0;
+    for (int n = 0; n < nloc; ++n)
+      if (d.is_free[lo + n]) { cx += d.x[3 * (lo + n)]; cy += d.x[3 * (lo + n) + 1]; ++cnt; }
+    s_small[0] = cnt ? cx / cnt : 0.0; s_small[1] = cnt ? cy / cnt : 0.0;
+  }
+  __syncthreads();
+  for (int n = tid; n < nloc; n += T) {
+    const int i = lo + n;
+    const double * h = d.Hd + 6 * i, * dg = d.diag + 3 * i;
+    const double a00 = h[0] + dg[0] * inv_radius, a01 = h[1], a02 = h[2], a11 = h[3] + dg[1] * inv_radius, a12 = h[4],
+                 a22 = h[5] + dg[2] * inv_radius;
+    double * H = sH + 6 * n;
+    H[0] = a00; H[1] = a01; H[2] = a02; H[3] = a11; H[4] = a12; H[5] = a22;
+    const double c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+    const double c11 = a00 * a22 - a02 * a02, c12 = a01 * a02 - a00 * a12, c22 = a00 * a11 - a01 * a01;
+    const double id = 1.0 / (a00 * c00 + a01 * c01 + a02 * c02);
+    double * mi = sMi + 6 * n;
+    mi[0] = c00 * id; mi[1] = c01 * id; mi[2] = c02 * id; mi[3] = c11 * id; mi[4] = c12 * id; mi[5] = c22 * id;
+    // P~ block: rigid-body modes of the aggregate in Jacobi-scaled variables (y~ = y / s); zero for constant nodes
+    double * pt = sPt + 9 * n;
+    const double f = d.is_free[i] ? 1.0 : 0.0;
+    const double isx = f / d.scale[3 * i], isy = f / d.scale[3 * i + 1], ist = f / d.scale[3 * i + 2];
+    pt[0] = isx; pt[1] = 0;   pt[2] = -(d.x[3 * i + 1] - s_small[1]) * isx;
+    pt[3] = 0;   pt[4] = isy; pt[5] = (d.x[3 * i] - s_small[0]) * isy;
+    pt[6] = 0;   pt[7] = 0;   pt[8] = ist;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c.gPt[9 * (size_t)i + k] = pt[k];
+  }
+  // own exchange slots start empty
+  if (tid < 8) c.e1[((size_t)(tid >> 2) * G + I) * kSlotStride + (tid & 3)] = SENT;
+  if (tid < 4) c.e2[((size_t)(tid >> 1) * G + I) * kSlotStride + (tid & 1)] = SENT;
+  bar_target += G;
+  grid_barrier(c.bar, bar_target);   // gPt, empty slots visible everywhere
+
+  // ---- coarse operator: this CTA's 3 rows of Ac = P^T (H + D) P, then block Gauss-Jordan ----
+  for (int k = tid; k < 6 * nc; k += T) sAc[k] = 0.0;
+  __syncthreads();
+  for (int ct = tid; ct < G; ct += T) {   // a thread owns coarse column block ct; slots are visited in order: deterministic
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < nslots; ++s) {
+      const int j = sCol[s];
+      if (j / c.npc != ct) continue;
+      const double * B = sB + 9 * s, * pi = sPt + 9 * sNode[s];
+      double pj[9], w[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) pj[k] = ld_cg(c.gPt + 9 * (size_t)j + k);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) w[3 * r + q] = B[3 * r] * pj[q] + B[3 * r + 1] * pj[3 + q] + B[3 * r + 2] * pj[6 + q];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) acc[3 * r + q] += pi[r] * w[q] + pi[3 + r] * w[3 + q] + pi[6 + r] * w[6 + q];
+    }
+    if (ct == I) {   // diagonal blocks of own nodes
+      for (int n = 0; n < nloc; ++n) {
+        const double * H = sH + 6 * n, * pi = sPt + 9 * n;
+        double w[9];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          w[q] = H[0] * pi[q] + H[1] * pi[3 + q] + H[2] * pi[6 + q];
+          w[3 + q] = H[1] * pi[q] + H[3] * pi[3 + q] + H[4] * pi[6 + q];
+          w[6 + q] = H[2] * pi[q] + H[4] * pi[3 + q] + H[5] * pi[6 + q];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q) acc[3 * r + q] += pi[r] * w[q] + pi[3 + r] * w[3 + q] + pi[6 + r] * w[6 + q];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) sAc[(size_t)r * 2 * nc + 3 * ct + q] = acc[3 * r + q];
+  }
+  if (tid < 3) sAc[(size_t)tid * 2 * nc + nc + 3 * I + tid] = 1.0;   // augmented identity
+  __syncthreads();
+  if (I == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_setup));
+  for (int k = 0; k < G; ++k) {
+    double * row = c.gRow + (size_t)k * 6 * nc;
+    if (I == k) {
+      // pivot block inverse (an aggregate without free nodes has a zero block: treat it as identity)
+      if (tid == 0) {
+        const double a00 = sAc[3 * k], a01 = sAc[3 * k + 1], a02 = sAc[3 * k + 2];
+        const double a10 = sAc[2 * nc + 3 * k], a11 = sAc[2 * nc + 3 * k + 1], a12 = sAc[2 * nc + 3 * k + 2];
+        const double a20 = sAc[4 * nc + 3 * k], a21 = sAc[4 * nc + 3 * k + 1], a22 = sAc[4 * nc + 3 * k + 2];
+        const double c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+        const double c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
+        const double c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
+        const double det = a00 * c00 + a01 * c10 + a02 * c20;
+        if (fabs(det) > 1e-300) {
+          const double id = 1.0 / det;
+          s_small[0] = c00 * id; s_small[1] = c01 * id; s_small[2] = c02 * id;
+          s_small[3] = c10 * id; s_small[4] = c11 * id; s_small[5] = c12 * id;
+          s_small[6] = c20 * id; s_small[7] = c21 * id; s_small[8] = c22 * id;
+        } else {
+          for (int q = 0; q < 9; ++q) s_small[q] = (q % 4 == 0) ? 1.0 : 0.0;
+        }
+      }
+      __syncthreads();
+      for (int j = tid; j < 2 * nc; j += T) {
+        const double v0 = sAc[j], v1 = sAc[2 * nc + j], v2 = sAc[4 * nc + j];
+        const double n0 = s_small[0] * v0 + s_small[1] * v1 + s_small[2] * v2;
+        const double n1 = s_small[3] * v0 + s_small[4] * v1 + s_small[5] * v2;
+        const double n2 = s_small[6] * v0 + s_small[7] * v1 + s_small[8] * v2;
+        sAc[j] = n0; sAc[2 * nc + j] = n1; sAc[4 * nc + j] = n2;
+        row[j] = n0; row[2 * nc + j] = n1; row[4 * nc + j] = n2;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(c.gjflag + k), "r"(1u) : "memory");
+      }
+    } else {
+      if (tid == 0) {
+        unsigned int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.gjflag + k) : "memory");
+        } while (v == 0u);
+        for (int q = 0; q < 9; ++q) s_small[q] = sAc[(size_t)(q / 3) * 2 * nc + 3 * k + (q % 3)];   // my multipliers
+      }
+      __syncthreads();
+      for (int j = tid; j < 2 * nc; j += T) {
+        const double r0 = ld_cg(row + j), r1 = ld_cg(row + 2 * nc + j), r2 = ld_cg(row + 4 * nc + j);
+        sAc[j] -= s_small[0] * r0 + s_small[1] * r1 + s_small[2] * r2;
+        sAc[2 * nc + j] -= s_small[3] * r0 + s_small[4] * r1 + s_small[5] * r2;
+        sAc[4 * nc + j] -= s_small[6] * r0 + s_small[7] * r1 + s_small[8] * r2;
+      }
+      __syncthreads();
+    }
+  }
+  if (I == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_gj));
+  // rows of Ac^-1 are now sAc[r * 2 nc + nc + j]
+  const double * Ai0 = sAc + nc, * Ai1 = sAc + 2 * nc + nc, * Ai2 = sAc + 4 * nc + nc;
+
+  // ---- CG start: r = b, coarse residual, z = M^-1 r ----
+  double accb[1] = {0};
+  for (int k = tid; k < 3 * nloc; k += T) {
+    const double b = d.g[3 * lo + k];
+    sR[k] = b; sY[k] = 0.0; sP[k] = 0.0;
+    c.gp[3 * lo + k] = 0.0;
+    accb[0] += b * b;
+  }
+  __syncthreads();
+  if (tid < 3) {
+    double a = 0;
+    for (int n = 0; n < nloc; ++n) a += sPt[9 * n + tid] * sR[3 * n] + sPt[9 * n + 3 + tid] * sR[3 * n + 1] + sPt[9 * n + 6 + tid] * sR[3 * n + 2];
+    c.grc[3 * I + tid] = a;
+  }
+  block_sum<1>(accb, red);
+  if (tid == 0) d.partial[I] = accb[0];
+  bar_target += G;
+  grid_barrier(c.bar, bar_target);
+  const double bb = grid_total(d, 0, G, bc);
+  for (int k = tid; k < nc; k += T) sRc[k] = ld_cg(c.grc + k);
+  __syncthreads();
+
+  // z = blockJacobi^-1 r + P Ac^-1 rc ; returns partial r.z and r.r through a2
+  auto apply_precond = [&](double (&a2)[2]) {
+    if (tid < 96) {   // 3 warps: one row of Ac^-1 each
+      const int w = tid >> 5, l = tid & 31;
+      const double * Ai = w == 0 ? Ai0 : (w == 1 ? Ai1 : Ai2);
+      double a = 0;
+      for (int j = l; j < nc; j += 32) a += Ai[j] * sRc[j];
+      a = warp_sum(a);
+      if (l == 0) s_small[12 + w] = a;
+    }
+    __syncthreads();
+    const double y0 = s_small[12], y1 = s_small[13], y2 = s_small[14];
+    a2[0] = 0; a2[1] = 0;
+    for (int k = tid; k < 3 * nloc; k += T) {
+      const int n = k / 3, r = k - 3 * n;
+      const double * mi = sMi + 6 * n, * pt = sPt + 9 * n + 3 * r;
+      const double r0 = sR[3 * n], r1 = sR[3 * n + 1], r2 = sR[3 * n + 2];
+      double z;
+      if (r == 0) z = mi[0] * r0 + mi[1] * r1 + mi[2] * r2;
+      else if (r == 1) z = mi[1] * r0 + mi[3] * r1 + mi[4] * r2;
+      else z = mi[2] * r0 + mi[4] * r1 + mi[5] * r2;
+      z += pt[0] * y0 + pt[1] * y1 + pt[2] * y2;
+      sZ[k] = z;
+      c.gz[3 * lo + k] = z;
+      a2[0] += sR[k] * z;
+      a2[1] += sR[k] * sR[k];
+    }
+  };
+  double a2[2];
+  apply_precond(a2);
+  block_sum<2>(a2, red);
+  if (tid == 0) d.partial[kMaxPartials + I] = a2[0];
+  bar_target += G;
+  grid_barrier(c.bar, bar_target);
+  double rz = grid_total(d, 1, G, bc);
+  double rr = bb;
+  const double stop = tol * tol * bb;
+  int it = 0;
+  double beta = 0.0;
+  int cur = 0;
+  if (bb > 0.0) {
+    while (it < max_iter) {
+      const int par = it & 1;
+      const double * gpo = c.gp + (size_t)cur * 3 * d.N;
+      double * gpn = c.gp + (size_t)(cur ^ 1) * 3 * d.N;
+      double * e1 = c.e1 + (size_t)par * G * kSlotStride, * e2 = c.e2 + (size_t)par * G * kSlotStride;
+      // ---- phase A ----
+      for (int s = tid; s < nslots; s += T) {
+        const int j = sCol[s];
+        double v0, v1, v2;
+        if (j >= lo && j < hi) {
+          const int n = j - lo;
+          v0 = sZ[3 * n] + beta * sP[3 * n]; v1 = sZ[3 * n + 1] + beta * sP[3 * n + 1]; v2 = sZ[3 * n + 2] + beta * sP[3 * n + 2];
+        } else {
+          v0 = ld_cg(c.gz + 3 * j) + beta * ld_cg(gpo + 3 * j);
+          v1 = ld_cg(c.gz + 3 * j + 1) + beta * ld_cg(gpo + 3 * j + 1);
+          v2 = ld_cg(c.gz + 3 * j + 2) + beta * ld_cg(gpo + 3 * j + 2);
+        }
+        sV[3 * s] = v0; sV[3 * s + 1] = v1; sV[3 * s + 2] = v2;
+      }
+      __syncthreads();
+      for (int k = tid; k < 3 * nloc; k += T) sQ[k] = sZ[k] + beta * sP[k];
+      __syncthreads();
+      for (int k = tid; k < 3 * nloc; k += T) { sP[k] = sQ[k]; gpn[3 * lo + k] = sQ[k]; }
+      __syncthreads();
+      double a1[4] = {0, 0, 0, 0};   // p.q and the three components of P^T q of this aggregate
+      for (int k = tid; k < 3 * nloc; k += T) {
+        const int n = k / 3, r = k - 3 * n;
+        const double * H = sH + 6 * n;
+        const double p0 = sP[3 * n], p1 = sP[3 * n + 1], p2 = sP[3 * n + 2];
+        double q;
+        if (r == 0) q = H[0] * p0 + H[1] * p1 + H[2] * p2;
+        else if (r == 1) q = H[1] * p0 + H[3] * p1 + H[4] * p2;
+        else q = H[2] * p0 + H[4] * p1 + H[5] * p2;
+        for (int s = sStart[n]; s < sStart[n + 1]; ++s) {
+          const double * B = sB + 9 * s + 3 * r, * v = sV + 3 * s;
+          q += B[0] * v[0] + B[1] * v[1] + B[2] * v[2];
+        }
+        sQ[k] = q;
+        const double * pt = sPt + 9 * n + 3 * r;
+        a1[0] += sP[k] * q;
+        a1[1] += pt[0] * q; a1[2] += pt[1] * q; a1[3] += pt[2] * q;
+      }
+      block_sum<4>(a1, red);
+      if (tid == 0) {
+        __threadfence();   // p_new of this CTA visible before the flagged values
+        double * m = e1 + (size_t)I * kSlotStride;
+        m[1] = a1[1]; m[2] = a1[2]; m[3] = a1[3];
+        m[0] = a1[0];
+      }
+      poll_slots<4>(e1, G, sEx);
+      // every CTA published E1(it) only after it finished reading E2(it-1): those slots can be recycled now
+      if (it > 0 && tid < 2) c.e2[((size_t)(par ^ 1) * G + I) * kSlotStride + tid] = SENT;
+      const double pq = ordered_sum(sEx, G, 4, 0, bc);
+      const double alpha = rz / pq;
+      // ---- phase B ----
+      for (int k = tid; k < nc; k += T) sRc[k] -= alpha * sEx[4 * (k / 3) + 1 + (k % 3)];
+      for (int k = tid; k < 3 * nloc; k += T) { sY[k] += alpha * sP[k]; sR[k] -= alpha * sQ[k]; }
+      __syncthreads();
+      apply_precond(a2);
+      block_sum<2>(a2, red);
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();   // z of this CTA visible before the flagged values
+        double * m = e2 + (size_t)I * kSlotStride;
+        m[0] = a2[0]; m[1] = a2[1];
+      }
+      poll_slots<2>(e2, G, sEx);
+      // every CTA published E2(it) only after it finished reading E1(it): recycle own E1(it) slots
+      if (tid < 4) c.e1[((size_t)par * G + I) * kSlotStride + tid] = SENT;
+      if (tid < 32) {
+        double u = 0, w = 0;
+        for (int i = tid; i < G; i += 32) { u += sEx[2 * i]; w += sEx[2 * i + 1]; }
+        u = warp_sum(u); w = warp_sum(w);
+        if (tid == 0) { s_small[10] = u; s_small[11] = w; }
+      }
+      __syncthreads();
+      const double rz_new = s_small[10];
+      rr = s_small[11];
+      ++it;
+      cur ^= 1;
+      if (!(rr > stop) || !(pq > 0.0)) break;
+      beta = rz_new / rz;
+      rz = rz_new;
+    }
+  }
+  for (int k = tid; k < 3 * nloc; k += T) d.y[3 * lo + k] = sY[k];
+  if (I == 0 && tid == 0) {
+    unsigned long long t_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    d.scalars[8] = (double)it;
+    d.scalars[9] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    d.scalars[10] = (double)(t_setup - t_start);   // ns: load rows + P~ + first barrier + Ac rows
+    d.scalars[11] = (double)(t_gj - t_setup);      // ns: block Gauss-Jordan
+    d.scalars[12] = (double)(t_end - t_gj);        // ns: CG iterations
+  }
+}
+
 // candidate point: delta = -(y * scale) ; xc = x (+) delta on free nodes; partial ||x - xc||^2
 __global__ void __launch_bounds__(kPgThreads) k_pg_apply_step(PgDev d)
 {
@@ -455,6 +1081,11 @@ struct b200pg {
   // device
   DevBuf<int32_t> d_eidx, d_adj_start, d_adj;
   DevBuf<uint8_t> d_free;
+  DevBuf<double> d_gz, d_gp, d_gPt, d_gRow, d_grc, d_e1, d_e2;
+  bool debug = false;
+  int precond = 1;   // 1 = two-level (rigid-mode aggregation) + block Jacobi, 0 = block Jacobi only
+  DevBuf<unsigned int> d_bar;
+  bool force_global_pcg = false;
   DevBuf<double> d_z, d_U, d_x, d_xc, d_scale, d_lin, d_Hd, d_g, d_diag, d_y, d_pr, d_pz, d_pp0, d_pp1, d_pq, d_Minv,
     d_partial, d_scalars;
   PinBuf<double> h_scalars;
@@ -527,6 +1158,14 @@ struct Lm {
   b200pg * h;
   PgDev d;
   int blocksN, blocksE, pcg_blocks;
+  bool use_smem = false;
+  int smem_blocks = 0;
+  size_t smem_bytes = 0;
+  PcgSmemCfg cfg{};
+  bool use_2lvl = false;
+  int blocks2 = 0;
+  size_t smem2_bytes = 0;
+  Pcg2Cfg cfg2{};
   cudaStream_t st;
 
   double scalar(int slot)
@@ -638,6 +1277,56 @@ static int solve(b200pg * h, b200pg_summary * sum)
   L.blocksE = std::min(kMaxPartials, std::max(1, (E + kPgThreads - 1) / kPgThreads));
   L.pcg_blocks = std::max(1, std::min({kMaxPartials, sms * std::max(per_sm, 1), (N + kPgThreads - 1) / kPgThreads}));
 
+  {
+    // shared-memory-resident PCG when every CTA's rows fit (one CTA per SM, 512 threads)
+    const int G = std::min(sms, std::max(1, (N + 31) / 32));
+    const int npc = (N + G - 1) / G;
+    const int Gu = (N + npc - 1) / npc;
+    int max_slots = 0;
+    for (int c = 0; c < Gu; ++c) {
+      const int lo = c * npc, hi = std::min(N, lo + npc);
+      max_slots = std::max(max_slots, adj_start[hi] - adj_start[lo]);
+    }
+    max_slots = std::max(max_slots, 1);
+    const size_t bytes = ((size_t)max_slots * 12 + (size_t)npc * 27) * sizeof(double) + ((size_t)max_slots + npc + 1) * sizeof(int) + 16;
+    if (bytes <= 200 * 1024 && !h->force_global_pcg) {
+      L.use_smem = true; L.smem_blocks = Gu; L.smem_bytes = bytes;
+      h->d_gz.reserve(n3); h->d_gp.reserve(2 * n3); h->d_bar.reserve(4096);
+      L.cfg.npc = npc; L.cfg.max_slots = max_slots; L.cfg.gz = h->d_gz.p; L.cfg.gp = h->d_gp.p; L.cfg.bar = h->d_bar.p;
+      B200_CUDA(cudaFuncSetAttribute(k_pg_pcg_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+  }
+  if (h->precond == 1 && !h->force_global_pcg) {
+    // two-level preconditioner: one aggregate per 256-thread CTA; prefer two CTAs per SM (smaller aggregates
+    // -> fewer CG iterations), fall back to one per SM when shared memory does not allow two
+    for (int per_sm = 2; per_sm >= 1 && !L.use_2lvl; --per_sm) {
+      const int G2 = std::min(per_sm * sms, std::max(1, (N + 15) / 16));
+      const int npc = (N + G2 - 1) / G2;
+      const int Gu = (N + npc - 1) / npc;
+      int max_slots = 1;
+      for (int c = 0; c < Gu; ++c) {
+        const int lo = c * npc, hi = std::min(N, lo + npc);
+        max_slots = std::max(max_slots, adj_start[hi] - adj_start[lo]);
+      }
+      const int nc = 3 * Gu;
+      const size_t bytes2 = ((size_t)max_slots * 12 + (size_t)npc * 36 + (size_t)7 * nc + (size_t)4 * Gu) * sizeof(double) +
+                            ((size_t)2 * max_slots + npc + 1) * sizeof(int) + 16;
+      if (bytes2 > 220 * 1024) continue;
+      int occ = 0;
+      B200_CUDA(cudaFuncSetAttribute(k_pg_pcg_2lvl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2));
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pg_pcg_2lvl, 256, bytes2));
+      if (h->debug) fprintf(stderr, "[b200pg] two-level plan: %d aggregates of %d nodes, max %d blocks/CTA, %zu B smem, occupancy %d/SM\n", Gu, npc, max_slots, bytes2, occ);
+      if (occ * sms < Gu) continue;
+      L.use_2lvl = true; L.smem2_bytes = bytes2; L.blocks2 = Gu;
+      h->d_gz.reserve(n3); h->d_gp.reserve(2 * n3);
+      h->d_bar.reserve(std::max<size_t>(4096, (size_t)Gu + 4));
+      h->d_gPt.reserve(9 * (size_t)N); h->d_gRow.reserve((size_t)Gu * 6 * nc); h->d_grc.reserve(nc);
+      h->d_e1.reserve((size_t)2 * Gu * kSlotStride); h->d_e2.reserve((size_t)2 * Gu * kSlotStride);
+      Pcg2Cfg & c2 = L.cfg2;
+      c2.npc = npc; c2.max_slots = max_slots; c2.gz = h->d_gz.p; c2.gp = h->d_gp.p; c2.gPt = h->d_gPt.p; c2.gRow = h->d_gRow.p;
+      c2.grc = h->d_grc.p; c2.e1 = h->d_e1.p; c2.e2 = h->d_e2.p; c2.bar = h->d_bar.p; c2.gjflag = h->d_bar.p + 1;
+    }
+  }
   B200_CUDA(cudaEventRecord(h->ev0, st));
   // ---- iteration 0: evaluate, Jacobi scaling from the unscaled Jacobian ----
   k_pg_fill<<<64, 256, 0, st>>>(d.scale, 1.0, 3 * N); L.launched();
@@ -673,8 +1362,18 @@ static int solve(b200pg * h, b200pg_summary * sum)
     {
       double inv_radius = 1.0 / radius, tol = o.pcg_tolerance;
       int max_iter = o.pcg_max_iterations;
-      void * args[] = {&d, &inv_radius, &tol, &max_iter};
-      B200_CUDA(cudaLaunchCooperativeKernel((void *)k_pg_pcg, dim3(L.pcg_blocks), dim3(kPgThreads), args, 0, st));
+      if (L.use_2lvl) {
+        B200_CUDA(cudaMemsetAsync(h->d_bar.p, 0, (size_t)(L.blocks2 + 1) * sizeof(unsigned int), st));
+        void * args[] = {&d, &L.cfg2, &inv_radius, &tol, &max_iter};
+        B200_CUDA(cudaLaunchCooperativeKernel((void *)k_pg_pcg_2lvl, dim3(L.blocks2), dim3(256), args, L.smem2_bytes, st));
+      } else if (L.use_smem) {
+        B200_CUDA(cudaMemsetAsync(h->d_bar.p, 0, sizeof(unsigned int), st));
+        void * args[] = {&d, &L.cfg, &inv_radius, &tol, &max_iter};
+        B200_CUDA(cudaLaunchCooperativeKernel((void *)k_pg_pcg_smem, dim3(L.smem_blocks), dim3(512), args, L.smem_bytes, st));
+      } else {
+        void * args[] = {&d, &inv_radius, &tol, &max_iter};
+        B200_CUDA(cudaLaunchCooperativeKernel((void *)k_pg_pcg, dim3(L.pcg_blocks), dim3(kPgThreads), args, 0, st));
+      }
       h->launches++;
     }
     reuse_diagonal = true;
@@ -686,6 +1385,9 @@ static int solve(b200pg * h, b200pg_summary * sum)
     L.fetch();
     const double * sc = h->h_scalars.p;
     S.pcg_iterations += (int)sc[8];
+    if (h->debug && L.use_2lvl)
+      fprintf(stderr, "[b200pg] lm %d: pcg %d it, setup %.1f us, gauss-jordan %.1f us, cg %.1f us (%.2f us/it)\n", it, (int)sc[8],
+              sc[10] * 1e-3, sc[11] * 1e-3, sc[12] * 1e-3, sc[12] * 1e-3 / std::max(1.0, sc[8]));
     const double model_cost_change = sc[4], step_norm = sqrt(sc[5]), cand_cost = sc[1];
     const bool finite = std::isfinite(model_cost_change) && std::isfinite(cand_cost) && std::isfinite(sc[9]);
     const bool valid = finite && model_cost_change > 0.0;
@@ -779,6 +1481,9 @@ int b200pg_create(const b200pg_opts * opts, b200pg ** out)
     return B200_ERR_INVALID_ARG;
   }
   require_device();
+  if (const char * e = getenv("B200PG_FORCE_GLOBAL_PCG")) h->force_global_pcg = atoi(e) != 0;
+  if (const char * e = getenv("B200PG_DEBUG")) h->debug = atoi(e) != 0;
+  if (const char * e = getenv("B200PG_PRECOND")) h->precond = std::string(e) == "jacobi" ? 0 : 1;
   *out = h.release();
   return B200_OK;
   B200_GUARD_END

@@ -108,3 +108,31 @@ def test_removed_graph_equals_freshly_built_graph():
     s2 = build(g2)
     assert s1.Compute() and s2.Compute()
     assert np.array_equal(s1.GetCorrections()[1], s2.GetCorrections()[1])   # deterministic, no atomics
+
+
+def test_smem_and_global_pcg_kernels_agree(monkeypatch):
+    """The shared-memory-resident PCG kernel against the global-memory one (forced through the env switch)."""
+    g = synth.make_pose_graph(11, 1500, 4500, sigma_xy=0.03, sigma_th=0.01)
+    s1 = build(g)
+    assert s1.Compute()
+    monkeypatch.setenv("B200PG_FORCE_GLOBAL_PCG", "1")
+    s2 = build(g)
+    assert s2.Compute()
+    assert s1.summary.iterations == s2.summary.iterations
+    dxy, dth = diff(s1.GetCorrections()[1], s2.GetCorrections()[1])
+    assert dxy < 1e-7 and dth < 1e-8, (dxy, dth)
+
+
+def test_two_level_and_jacobi_preconditioners_agree(monkeypatch):
+    """Two-level (rigid-mode aggregation) PCG against block-Jacobi PCG: same LM trajectory, same poses to PCG accuracy,
+    far fewer CG iterations."""
+    g = synth.make_pose_graph(12, 4000, 14000, sigma_xy=0.03, sigma_th=0.01)
+    s1 = build(g)
+    assert s1.Compute()
+    monkeypatch.setenv("B200PG_PRECOND", "jacobi")
+    s2 = build(g)
+    assert s2.Compute()
+    assert s1.summary.iterations == s2.summary.iterations and s1.summary.successful_steps == s2.summary.successful_steps
+    dxy, dth = diff(s1.GetCorrections()[1], s2.GetCorrections()[1])
+    assert dxy < 1e-7 and dth < 1e-8, (dxy, dth)
+    assert s1.summary.pcg_iterations < 0.6 * s2.summary.pcg_iterations, (s1.summary.pcg_iterations, s2.summary.pcg_iterations)

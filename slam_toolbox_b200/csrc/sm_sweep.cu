@@ -499,11 +499,15 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
               }
             }
             b = ce;
-            // flush the 16-bit fields: pose x = x0 + t, t = 0..3
+            // flush the 16-bit fields: pose x = x0 + t, t = 0..3 (most windows of a sparse grid are empty)
+            uint32_t any = 0;
+#pragma unroll
+            for (int r = 0; r < kFastRowTiles; ++r) any |= T0[r] | T1[r];
+            if (!__any_sync(0xffffffffu, any != 0)) continue;
 #pragma unroll
             for (int r = 0; r < kFastRowTiles; ++r) {
               const int y = y_l + 8 * r;
-              if (y >= nY) continue;
+              if (y >= nY || (T0[r] | T1[r]) == 0) continue;
               int32_t * dst = Arow + y * nX + x0;
               const int v0 = T0[r] & 0xFFFF, v1 = T1[r] & 0xFFFF, v2 = T0[r] >> 16, v3 = T1[r] >> 16;
               if (v0 && (unsigned)(x0 + 0) < (unsigned)nX) atomicAdd(dst + 0, v0);

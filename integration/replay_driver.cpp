@@ -1,0 +1,130 @@
+// cfg3 replay driver: the reference's own karto::Mapper::Process (Mapper.cpp:2679-2749) fed with posed
+// scans, with the GPU ScanSolver adapter installed through Mapper::SetScanSolver and -- when linked into
+// libreplay_b200.so -- every MatchScan redirected to the GPU by scan_matcher_b200.cpp.
+// libreplay_ref.so is the same driver linked WITHOUT the matcher shim (reference CPU matcher).
+#include <chrono>
+#include <string>
+
+#include "karto_sdk/Mapper.h"
+#include "b200_solver.hpp"
+
+using namespace karto;
+
+namespace {
+struct Replay {
+  Mapper mapper;
+  solver_plugins::B200Solver * solver = nullptr;
+  std::vector<LocalizedRangeScan *> scans;
+  double process_seconds = 0.0;
+  int processed = 0;
+};
+const char * kLaser = "laser0";
+}
+
+extern "C" {
+
+int krep_init_laser(double min_angle, double max_angle, double ang_res, double min_range, double max_range, double range_threshold)
+{
+  Name nm(kLaser);
+  LaserRangeFinder * l = LaserRangeFinder::CreateLaserRangeFinder(LaserRangeFinder_Custom, nm);
+  l->SetMinimumRange(min_range); l->SetMaximumRange(max_range);
+  l->SetMinimumAngle(min_angle); l->SetMaximumAngle(max_angle);
+  l->SetAngularResolution(ang_res); l->SetRangeThreshold(range_threshold);
+  l->SetOffsetPose(Pose2(0.0, 0.0, 0.0));
+  SensorManager::GetInstance()->RegisterSensor(l);
+  return static_cast<int>(l->GetNumberOfRangeReadings());
+}
+
+void * krep_create(int use_solver)
+{
+  Replay * r = new Replay();
+  if (use_solver) {
+    r->solver = new solver_plugins::B200Solver();
+    r->mapper.SetScanSolver(r->solver);
+  }
+  return r;
+}
+
+int krep_set(void * rp, const char * name, double v)
+{
+  Mapper * m = &static_cast<Replay *>(rp)->mapper;
+  std::string n(name);
+  if (n == "coarse_search_angle_offset") m->setParamCoarseSearchAngleOffset(v);
+  else if (n == "coarse_angle_resolution") m->setParamCoarseAngleResolution(v);
+  else if (n == "fine_search_angle_offset") m->setParamFineSearchAngleOffset(v);
+  else if (n == "distance_variance_penalty") m->setParamDistanceVariancePenalty(v);
+  else if (n == "angle_variance_penalty") m->setParamAngleVariancePenalty(v);
+  else if (n == "minimum_distance_penalty") m->setParamMinimumDistancePenalty(v);
+  else if (n == "minimum_angle_penalty") m->setParamMinimumAnglePenalty(v);
+  else if (n == "use_response_expansion") m->setParamUseResponseExpansion(v != 0.0);
+  else if (n == "correlation_search_space_dimension") m->setParamCorrelationSearchSpaceDimension(v);
+  else if (n == "correlation_search_space_resolution") m->setParamCorrelationSearchSpaceResolution(v);
+  else if (n == "correlation_search_space_smear_deviation") m->setParamCorrelationSearchSpaceSmearDeviation(v);
+  else if (n == "loop_search_space_dimension") m->setParamLoopSearchSpaceDimension(v);
+  else if (n == "loop_search_space_resolution") m->setParamLoopSearchSpaceResolution(v);
+  else if (n == "loop_search_space_smear_deviation") m->setParamLoopSearchSpaceSmearDeviation(v);
+  else if (n == "minimum_travel_distance") m->setParamMinimumTravelDistance(v);
+  else if (n == "minimum_travel_heading") m->setParamMinimumTravelHeading(v);
+  else if (n == "scan_buffer_size") m->setParamScanBufferSize(static_cast<int>(v));
+  else if (n == "scan_buffer_maximum_scan_distance") m->setParamScanBufferMaximumScanDistance(v);
+  else if (n == "link_match_minimum_response_fine") m->setParamLinkMatchMinimumResponseFine(v);
+  else if (n == "link_scan_maximum_distance") m->setParamLinkScanMaximumDistance(v);
+  else if (n == "loop_search_maximum_distance") m->setParamLoopSearchMaximumDistance(v);
+  else if (n == "do_loop_closing") m->setParamDoLoopClosing(v != 0.0);
+  else if (n == "loop_match_minimum_chain_size") m->setParamLoopMatchMinimumChainSize(static_cast<int>(v));
+  else if (n == "loop_match_maximum_variance_coarse") m->setParamLoopMatchMaximumVarianceCoarse(v);
+  else if (n == "loop_match_minimum_response_coarse") m->setParamLoopMatchMinimumResponseCoarse(v);
+  else if (n == "loop_match_minimum_response_fine") m->setParamLoopMatchMinimumResponseFine(v);
+  else if (n == "use_scan_matching") m->setParamUseScanMatching(v != 0.0);
+  else if (n == "use_scan_barycenter") m->setParamUseScanBarycenter(v != 0.0);
+  else if (n == "minimum_time_interval") m->setParamMinimumTimeInterval(v);
+  else return -1;
+  return 0;
+}
+
+// feeds one scan with its odometric pose; returns 1 if the mapper processed (kept) it
+int krep_process(void * rp, const double * ranges, int n, const double odom[3], int id)
+{
+  Replay * r = static_cast<Replay *>(rp);
+  RangeReadingsVector rr(ranges, ranges + n);
+  LocalizedRangeScan * s = new LocalizedRangeScan(Name(kLaser), rr);
+  Pose2 p(odom[0], odom[1], odom[2]);
+  s->SetOdometricPose(p);
+  s->SetCorrectedPose(p);
+  s->SetTime(static_cast<double>(id));
+  auto t0 = std::chrono::steady_clock::now();
+  bool ok = false;
+  try {
+    ok = r->mapper.Process(s);
+  } catch (const std::exception & e) {
+    std::fprintf(stderr, "krep_process: %s\n", e.what());
+  }
+  r->process_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (ok) { r->scans.push_back(s); ++r->processed; } else { delete s; }
+  return ok ? 1 : 0;
+}
+
+int krep_num_scans(void * rp) { return static_cast<int>(static_cast<Replay *>(rp)->scans.size()); }
+
+// corrected poses (after all loop closures) of the processed scans, in processing order
+void krep_poses(void * rp, double * out)
+{
+  Replay * r = static_cast<Replay *>(rp);
+  for (size_t i = 0; i < r->scans.size(); ++i) {
+    const Pose2 & p = r->scans[i]->GetCorrectedPose();
+    out[3 * i] = p.GetX(); out[3 * i + 1] = p.GetY(); out[3 * i + 2] = p.GetHeading();
+  }
+}
+
+// stats: process seconds, solver computes, solver device ms, graph edges, graph vertices
+void krep_stats(void * rp, double out[5])
+{
+  Replay * r = static_cast<Replay *>(rp);
+  out[0] = r->process_seconds;
+  out[1] = r->solver ? r->solver->computes() : 0;
+  out[2] = r->solver ? r->solver->solve_ms() : 0;
+  out[3] = static_cast<double>(r->mapper.GetGraph() ? r->mapper.GetGraph()->GetEdges().size() : 0);
+  out[4] = static_cast<double>(r->scans.size());
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Reference-side binding #2: link-time replacement of
+// karto::ScanMatcher::Create and karto::ScanMatcher::MatchScan<T> by the b200slam C ABI.
+//
+// Mapper.o reaches both through PLT relocations by symbol name (objdump -dr: 3 x Create, 8 x MatchScan),
+// so linking THIS object ahead of the unmodified Mapper.o (with -Wl,--allow-multiple-definition for the
+// strong Create; the MatchScan instantiations in Mapper.o are weak) redirects every match the
+// reference's Mapper / MapperGraph performs -- sequential match, near-chain links, loop closure --
+// to the GPU, with no change to the reference sources.
+#include <cstdio>
+#include <stdexcept>
+#include <unordered_map>
+#include <vector>
+
+#include "karto_sdk/Mapper.h"
+#include "b200slam.h"
+
+namespace karto {
+
+namespace {
+std::unordered_map<const ScanMatcher *, b200sm *> & handles()
+{
+  static std::unordered_map<const ScanMatcher *, b200sm *> h;
+  return h;
+}
+long g_match_calls = 0;
+
+b200_scan to_scan(LocalizedRangeScan * s)
+{
+  b200_scan o;
+  const PointVectorDouble & pts = s->GetPointReadings(false);   // unfiltered (Karto.h:5613-5628)
+  o.n = static_cast<int32_t>(s->GetNumberOfRangeReadings());
+  o.ranges = s->GetRangeReadings();
+  static_assert(sizeof(Vector2<kt_double>) == 2 * sizeof(double), "Vector2<double> must be {x, y}");
+  o.points_xy = reinterpret_cast<const double *>(pts.data());
+  const Pose2 p = s->GetSensorPose();
+  o.sensor_pose[0] = p.GetX(); o.sensor_pose[1] = p.GetY(); o.sensor_pose[2] = p.GetHeading();
+  return o;
+}
+inline LocalizedRangeScan * deref(LocalizedRangeScanVector::const_iterator it) { return *it; }
+inline LocalizedRangeScan * deref(LocalizedRangeScanMap::const_iterator it) { return it->second; }
+}  // namespace
+
+extern "C" long b200_shim_match_calls() { return g_match_calls; }
+
+ScanMatcher * ScanMatcher::Create(Mapper * pMapper, kt_double searchSize, kt_double resolution,
+                                  kt_double smearDeviation, kt_double rangeThreshold)
+{
+  b200sm_params p{searchSize, resolution, smearDeviation, rangeThreshold,
+      pMapper->m_pCoarseSearchAngleOffset->GetValue(), pMapper->m_pCoarseAngleResolution->GetValue(),
+      pMapper->m_pFineSearchAngleOffset->GetValue(), pMapper->m_pDistanceVariancePenalty->GetValue(),
+      pMapper->m_pAngleVariancePenalty->GetValue(), pMapper->m_pMinimumDistancePenalty->GetValue(),
+      pMapper->m_pMinimumAnglePenalty->GetValue(), pMapper->m_pUseResponseExpansion->GetValue() ? 1 : 0};
+  b200sm * h = nullptr;
+  if (b200sm_create(&p, &h) != B200_OK) {
+    std::fprintf(stderr, "ScanMatcher::Create (b200): %s\n", b200_last_error());
+    return NULL;   // Mapper.cpp:481-493 returns NULL on invalid parameters
+  }
+  ScanMatcher * m = new ScanMatcher(pMapper);
+  handles()[m] = h;
+  return m;
+}
+
+template<class T>
+kt_double ScanMatcher::MatchScan(LocalizedRangeScan * pScan, const T & rBaseScans, Pose2 & rMean,
+                                 Matrix3 & rCovariance, kt_bool doPenalize, kt_bool doRefineMatch)
+{
+  ++g_match_calls;
+  std::vector<b200_scan> base;
+  for (auto it = rBaseScans.begin(); it != rBaseScans.end(); ++it) {
+    LocalizedRangeScan * s = deref(it);
+    if (s) base.push_back(to_scan(s));   // NULL scans are skipped (Mapper.cpp:1039); order preserved
+  }
+  const b200_scan q = to_scan(pScan);
+  double mean[3], cov[9], resp = 0.0;
+  if (b200sm_match(handles().at(this), &q, base.data(), static_cast<int32_t>(base.size()), doPenalize ? 1 : 0,
+                   doRefineMatch ? 1 : 0, mean, cov, &resp) != B200_OK) {
+    throw std::runtime_error(b200_last_error());   // the reference throws std::runtime_error too (Mapper.cpp:789-828)
+  }
+  rMean = Pose2(mean[0], mean[1], mean[2]);
+  // MatchScan leaves entries it does not compute untouched; the callers pass zero / identity matrices and
+  // the ABI returns the full matrix the reference would have produced from a zero-initialised one
+  for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) rCovariance(r, k) = cov[3 * r + k];
+  return resp;
+}
+
+template kt_double ScanMatcher::MatchScan<LocalizedRangeScanVector>(LocalizedRangeScan *, const LocalizedRangeScanVector &,
+                                                                    Pose2 &, Matrix3 &, kt_bool, kt_bool);
+template kt_double ScanMatcher::MatchScan<LocalizedRangeScanMap>(LocalizedRangeScan *, const LocalizedRangeScanMap &,
+                                                                 Pose2 &, Matrix3 &, kt_bool, kt_bool);
+
+}  // namespace karto

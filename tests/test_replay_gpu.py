@@ -1,0 +1,40 @@
+"""cfg3 (reduced): the reference's own karto::Mapper::Process replayed over a posed-scan sequence, once with the
+reference CPU ScanMatcher and once with every MatchScan redirected to the GPU through the link-time seam
+(integration/scan_matcher_b200.cpp), both with the GPU ScanSolver adapter installed. Because the GPU matcher is
+bit-identical to the reference, the two SLAM runs must produce identical graphs and identical poses."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "integration"))
+import replay  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not replay.available(), reason="integration/_build/*.so not built")]
+
+
+def test_mapper_process_replay_is_identical_with_the_gpu_matcher():
+    ranges, odom, truth = replay.make_trajectory(4, 120)
+    params = dict(replay.YAML_PARAMS, correlation_search_space_smear_deviation=0.03, loop_search_space_dimension=4.0)
+    a = replay.run("ref", ranges, odom, params)
+    b = replay.run("b200", ranges, odom, params)
+    assert a["scans"] == b["scans"] and a["scans"] > 50
+    assert np.array_equal(a["kept"], b["kept"])
+    assert a["edges"] == b["edges"] and a["solver_computes"] == b["solver_computes"]
+    assert np.array_equal(a["poses"], b["poses"])
+    assert b["match_calls"] >= b["scans"] - 1
+    # the matcher actually corrected the drifting odometry
+    kept = a["kept"]
+    err_odo = np.abs(odom[kept, :2] - truth[kept, :2]).max()
+    err_slam = np.abs(a["poses"][:, :2] - truth[kept, :2] - (a["poses"][0, :2] - truth[kept[0], :2])).max()
+    assert err_slam < err_odo
+
+
+def test_replay_with_the_shipped_yaml_parameters_order_dependent_raster():
+    """smear 0.1 m @ 0.01 m (config/mapper_params_online_sync.yaml): the raster depends on insertion order."""
+    ranges, odom, _ = replay.make_trajectory(5, 40)
+    a = replay.run("ref", ranges, odom, replay.YAML_PARAMS)
+    b = replay.run("b200", ranges, odom, replay.YAML_PARAMS)
+    assert a["scans"] == b["scans"] and np.array_equal(a["poses"], b["poses"]) and a["edges"] == b["edges"]

@@ -22,6 +22,7 @@ public:
   void Compute() override   // solvers/ceres_solver.cpp:214-269
   {
     ++computes_;
+    if (getenv("B200_TRACE")) fprintf(stderr, "Compute\n");
     b200pg_summary s;
     if (b200pg_solve(h_, &s) != B200_OK) return;   // unusable: corrections untouched, like the reference
     solve_ms_ += s.solve_ms;
@@ -40,6 +41,7 @@ public:
   void AddNode(karto::Vertex<karto::LocalizedRangeScan> * v) override   // ceres_solver.cpp:317-336
   {
     if (!v) return;
+    if (getenv("B200_TRACE")) fprintf(stderr, "AddNode %p\n", (void*)v);
     const karto::Pose2 p = v->GetObject()->GetCorrectedPose();
     const double pose[3] = {p.GetX(), p.GetY(), p.GetHeading()};
     b200pg_add_node(h_, v->GetObject()->GetUniqueId(), pose);
@@ -47,6 +49,7 @@ public:
   void AddConstraint(karto::Edge<karto::LocalizedRangeScan> * e) override   // ceres_solver.cpp:339-392
   {
     if (!e) return;
+    if (getenv("B200_TRACE")) fprintf(stderr, "AddConstraint %p label %p\n", (void*)e, (void*)e->GetLabel());
     karto::LinkInfo * li = static_cast<karto::LinkInfo *>(e->GetLabel());
     const karto::Pose2 d = li->GetPoseDifference();
     const karto::Matrix3 c = li->GetCovariance();

@@ -3,7 +3,11 @@
 // libreplay_b200.so -- every MatchScan redirected to the GPU by scan_matcher_b200.cpp.
 // libreplay_ref.so is the same driver linked WITHOUT the matcher shim (reference CPU matcher).
 #include <chrono>
+#include <csignal>
+#include <cstdlib>
+#include <execinfo.h>
 #include <string>
+#include <unistd.h>
 
 #include "karto_sdk/Mapper.h"
 #include "b200_solver.hpp"
@@ -21,10 +25,19 @@ struct Replay {
 const char * kLaser = "laser0";
 }
 
+static void segv_handler(int)
+{
+  void * frames[64];
+  int n = backtrace(frames, 64);
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(139);
+}
+
 extern "C" {
 
 int krep_init_laser(double min_angle, double max_angle, double ang_res, double min_range, double max_range, double range_threshold)
 {
+  if (getenv("B200_TRACE")) signal(SIGSEGV, segv_handler);
   Name nm(kLaser);
   LaserRangeFinder * l = LaserRangeFinder::CreateLaserRangeFinder(LaserRangeFinder_Custom, nm);
   l->SetMinimumRange(min_range); l->SetMaximumRange(max_range);

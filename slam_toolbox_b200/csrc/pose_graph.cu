@@ -684,6 +684,8 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
   unsigned int bar_target = 0;
   const double SENT = pg_sentinel();
   unsigned long long t_start = 0, t_setup = 0, t_gj = 0;
+  unsigned long long tA = 0, tB = 0, tC = 0, tD = 0, tE = 0, t0 = 0, t1 = 0;   // CG phase timers
+#define PG_TICK(acc) do { if (I == 0 && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); acc += t1 - t0; t0 = t1; } } while (0)
   if (I == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
 
   // ---- load this CTA's rows (as k_pg_pcg_smem) ----
@@ -914,6 +916,7 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
       double * gpn = c.gp + (size_t)(cur ^ 1) * 3 * d.N;
       double * e1 = c.e1 + (size_t)par * G * kSlotStride, * e2 = c.e2 + (size_t)par * G * kSlotStride;
       // ---- phase A ----
+      if (I == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
       for (int s = tid; s < nslots; s += T) {
         const int j = sCol[s];
         double v0, v1, v2;
@@ -928,6 +931,7 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
         sV[3 * s] = v0; sV[3 * s + 1] = v1; sV[3 * s + 2] = v2;
       }
       __syncthreads();
+      PG_TICK(tA);
       for (int k = tid; k < 3 * nloc; k += T) sQ[k] = sZ[k] + beta * sP[k];
       __syncthreads();
       for (int k = tid; k < 3 * nloc; k += T) { sP[k] = sQ[k]; gpn[3 * lo + k] = sQ[k]; }
@@ -951,6 +955,7 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
         a1[1] += pt[0] * q; a1[2] += pt[1] * q; a1[3] += pt[2] * q;
       }
       block_sum<4>(a1, red);
+      PG_TICK(tB);
       if (tid == 0) {
         __threadfence();   // p_new of this CTA visible before the flagged values
         double * m = e1 + (size_t)I * kSlotStride;
@@ -958,6 +963,7 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
         m[0] = a1[0];
       }
       poll_slots<4>(e1, G, sEx);
+      PG_TICK(tC);
       // every CTA published E1(it) only after it finished reading E2(it-1): those slots can be recycled now
       if (it > 0 && tid < 2) c.e2[((size_t)(par ^ 1) * G + I) * kSlotStride + tid] = SENT;
       const double pq = ordered_sum(sEx, G, 4, 0, bc);
@@ -969,12 +975,14 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
       apply_precond(a2);
       block_sum<2>(a2, red);
       __syncthreads();
+      PG_TICK(tD);
       if (tid == 0) {
         __threadfence();   // z of this CTA visible before the flagged values
         double * m = e2 + (size_t)I * kSlotStride;
         m[0] = a2[0]; m[1] = a2[1];
       }
       poll_slots<2>(e2, G, sEx);
+      PG_TICK(tE);
       // every CTA published E2(it) only after it finished reading E1(it): recycle own E1(it) slots
       if (tid < 4) c.e1[((size_t)par * G + I) * kSlotStride + tid] = SENT;
       if (tid < 32) {
@@ -1002,6 +1010,8 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
     d.scalars[10] = (double)(t_setup - t_start);   // ns: load rows + P~ + first barrier + Ac rows
     d.scalars[11] = (double)(t_gj - t_setup);      // ns: block Gauss-Jordan
     d.scalars[12] = (double)(t_end - t_gj);        // ns: CG iterations
+    d.scalars[13] = (double)tA; d.scalars[14] = (double)tB; d.scalars[15] = (double)tC;
+    d.scalars[6] = (double)tD; d.scalars[7] = (double)tE;
   }
 }
 
@@ -1386,8 +1396,9 @@ static int solve(b200pg * h, b200pg_summary * sum)
     const double * sc = h->h_scalars.p;
     S.pcg_iterations += (int)sc[8];
     if (h->debug && L.use_2lvl)
-      fprintf(stderr, "[b200pg] lm %d: pcg %d it, setup %.1f us, gauss-jordan %.1f us, cg %.1f us (%.2f us/it)\n", it, (int)sc[8],
-              sc[10] * 1e-3, sc[11] * 1e-3, sc[12] * 1e-3, sc[12] * 1e-3 / std::max(1.0, sc[8]));
+      fprintf(stderr, "[b200pg] lm %d: pcg %d it, setup %.1f us, gauss-jordan %.1f us, cg %.1f us (%.2f us/it: gather %.2f spmv+reduce %.2f exch1 %.2f precond %.2f exch2 %.2f)\n", it, (int)sc[8],
+              sc[10] * 1e-3, sc[11] * 1e-3, sc[12] * 1e-3, sc[12] * 1e-3 / std::max(1.0, sc[8]), sc[13] * 1e-3 / std::max(1.0, sc[8]),
+              sc[14] * 1e-3 / std::max(1.0, sc[8]), sc[15] * 1e-3 / std::max(1.0, sc[8]), sc[6] * 1e-3 / std::max(1.0, sc[8]), sc[7] * 1e-3 / std::max(1.0, sc[8]));
     const double model_cost_change = sc[4], step_norm = sqrt(sc[5]), cand_cost = sc[1];
     const bool finite = std::isfinite(model_cost_change) && std::isfinite(cand_cost) && std::isfinite(sc[9]);
     const bool valid = finite && model_cost_change > 0.0;

@@ -590,7 +590,10 @@ __global__ void __launch_bounds__(512, 1) k_pg_pcg_smem(PgDev d, PcgSmemCfg c, d
 // All reductions are summed in a fixed order: results are bit-reproducible.
 // ------------------------------------------------------------------------------------------
 struct Pcg2Cfg {
-  int npc, max_slots;
+  int npc, max_slots;     // npc = MAX nodes of one aggregate (array sizing)
+  int ex_doubles;         // size of the exchange scratch (>= 4 G and large enough for the set-up alias)
+  const int32_t * agg_start;   // [G + 1] contiguous node ranges, balanced by block count
+  const int32_t * agg_of;      // [N] aggregate of every node
   double * gz;            // [N][3]
   double * gp;            // [2][N][3]
   double * gPt;           // [N][9]   P~ block of every node (rows: node comps, cols: coarse comps)
@@ -663,11 +666,12 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
   __shared__ double s_small[16];
   const int T = blockDim.x, tid = threadIdx.x, G = gridDim.x, I = blockIdx.x;
   const int nc = 3 * G;
-  const int lo = min(d.N, I * c.npc), hi = min(d.N, lo + c.npc), nloc = hi - lo;
+  const int lo = c.agg_start[I], hi = c.agg_start[I + 1], nloc = hi - lo;
   const int s_lo = d.adj_start[lo], nslots = d.adj_start[hi] - s_lo;
   double * sB = reinterpret_cast<double *>(sm_raw);            // [max_slots][9]
   double * sV = sB + (size_t)c.max_slots * 9;                  // [max_slots][3]
-  double * sH = sV + (size_t)c.max_slots * 3;                  // [npc][6]
+  double * sEx = sV + (size_t)c.max_slots * 3;                 // [ex_doubles >= 4 G] exchange scratch, right after sV
+  double * sH = sEx + (size_t)c.ex_doubles;                    // [npc][6]
   double * sMi = sH + (size_t)c.npc * 6;                       // [npc][6]
   double * sR = sMi + (size_t)c.npc * 6;                       // [npc][3] each below
   double * sZ = sR + (size_t)c.npc * 3;
@@ -675,10 +679,12 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
   double * sQ = sP + (size_t)c.npc * 3;
   double * sY = sQ + (size_t)c.npc * 3;
   double * sPt = sY + (size_t)c.npc * 3;                       // [npc][9]
-  double * sAc = sPt + (size_t)c.npc * 9;                      // [3][2 nc] -> right half becomes rows of Ac^-1
-  double * sRc = sAc + (size_t)6 * nc;                         // [nc] coarse residual (identical in all CTAs)
-  double * sEx = sRc + nc;                                     // [4 G] exchange scratch
-  int * sCol = reinterpret_cast<int *>(sEx + (size_t)4 * G);   // [max_slots]
+  double * sAr = sPt + (size_t)c.npc * 9;                      // [3][nc] right half of [Ac | I] -> rows of Ac^-1
+  double * sRc = sAr + (size_t)3 * nc;                         // [nc] coarse residual (identical in all CTAs)
+  // the left half of [Ac | I] only lives during set-up: it aliases the CG-only scratch sV | sEx
+  // (3 max_slots + ex_doubles >= 3 nc is guaranteed by the host)
+  double * sAl = sV;                                           // [3][nc]
+  int * sCol = reinterpret_cast<int *>(sRc + nc);              // [max_slots]
   int * sNode = sCol + c.max_slots;                            // [max_slots] local node of the slot
   int * sStart = sNode + c.max_slots;                          // [npc + 1]
   unsigned int bar_target = 0;
@@ -746,13 +752,13 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
   grid_barrier(c.bar, bar_target);   // gPt, empty slots visible everywhere
 
   // ---- coarse operator: this CTA's 3 rows of Ac = P^T (H + D) P, then block Gauss-Jordan ----
-  for (int k = tid; k < 6 * nc; k += T) sAc[k] = 0.0;
+  for (int k = tid; k < 3 * nc; k += T) { sAl[k] = 0.0; sAr[k] = 0.0; }
   __syncthreads();
   for (int ct = tid; ct < G; ct += T) {   // a thread owns coarse column block ct; slots are visited in order: deterministic
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int s = 0; s < nslots; ++s) {
       const int j = sCol[s];
-      if (j / c.npc != ct) continue;
+      if (c.agg_of[j] != ct) continue;
       const double * B = sB + 9 * s, * pi = sPt + 9 * sNode[s];
       double pj[9], w[9];
 #pragma unroll
@@ -785,19 +791,20 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int q = 0; q < 3; ++q) sAc[(size_t)r * 2 * nc + 3 * ct + q] = acc[3 * r + q];
+      for (int q = 0; q < 3; ++q) sAl[(size_t)r * nc + 3 * ct + q] = acc[3 * r + q];
   }
-  if (tid < 3) sAc[(size_t)tid * 2 * nc + nc + 3 * I + tid] = 1.0;   // augmented identity
+  if (tid < 3) sAr[(size_t)tid * nc + 3 * I + tid] = 1.0;   // augmented identity
   __syncthreads();
   if (I == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_setup));
   for (int k = 0; k < G; ++k) {
-    double * row = c.gRow + (size_t)k * 6 * nc;
+    double * row = c.gRow + (size_t)k * 6 * nc;   // published pivot rows: [3][nc] left | [3][nc] right
+    auto elem = [&](int r, int j) -> double & { return j < nc ? sAl[(size_t)r * nc + j] : sAr[(size_t)r * nc + (j - nc)]; };
     if (I == k) {
       // pivot block inverse (an aggregate without free nodes has a zero block: treat it as identity)
       if (tid == 0) {
-        const double a00 = sAc[3 * k], a01 = sAc[3 * k + 1], a02 = sAc[3 * k + 2];
-        const double a10 = sAc[2 * nc + 3 * k], a11 = sAc[2 * nc + 3 * k + 1], a12 = sAc[2 * nc + 3 * k + 2];
-        const double a20 = sAc[4 * nc + 3 * k], a21 = sAc[4 * nc + 3 * k + 1], a22 = sAc[4 * nc + 3 * k + 2];
+        const double a00 = elem(0, 3 * k), a01 = elem(0, 3 * k + 1), a02 = elem(0, 3 * k + 2);
+        const double a10 = elem(1, 3 * k), a11 = elem(1, 3 * k + 1), a12 = elem(1, 3 * k + 2);
+        const double a20 = elem(2, 3 * k), a21 = elem(2, 3 * k + 1), a22 = elem(2, 3 * k + 2);
         const double c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
         const double c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
         const double c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
@@ -813,11 +820,11 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
       }
       __syncthreads();
       for (int j = tid; j < 2 * nc; j += T) {
-        const double v0 = sAc[j], v1 = sAc[2 * nc + j], v2 = sAc[4 * nc + j];
+        const double v0 = elem(0, j), v1 = elem(1, j), v2 = elem(2, j);
         const double n0 = s_small[0] * v0 + s_small[1] * v1 + s_small[2] * v2;
         const double n1 = s_small[3] * v0 + s_small[4] * v1 + s_small[5] * v2;
         const double n2 = s_small[6] * v0 + s_small[7] * v1 + s_small[8] * v2;
-        sAc[j] = n0; sAc[2 * nc + j] = n1; sAc[4 * nc + j] = n2;
+        elem(0, j) = n0; elem(1, j) = n1; elem(2, j) = n2;
         row[j] = n0; row[2 * nc + j] = n1; row[4 * nc + j] = n2;
       }
       __syncthreads();
@@ -831,21 +838,22 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.gjflag + k) : "memory");
         } while (v == 0u);
-        for (int q = 0; q < 9; ++q) s_small[q] = sAc[(size_t)(q / 3) * 2 * nc + 3 * k + (q % 3)];   // my multipliers
+        for (int q = 0; q < 9; ++q) s_small[q] = elem(q / 3, 3 * k + (q % 3));   // my multipliers
       }
       __syncthreads();
       for (int j = tid; j < 2 * nc; j += T) {
         const double r0 = ld_cg(row + j), r1 = ld_cg(row + 2 * nc + j), r2 = ld_cg(row + 4 * nc + j);
-        sAc[j] -= s_small[0] * r0 + s_small[1] * r1 + s_small[2] * r2;
-        sAc[2 * nc + j] -= s_small[3] * r0 + s_small[4] * r1 + s_small[5] * r2;
-        sAc[4 * nc + j] -= s_small[6] * r0 + s_small[7] * r1 + s_small[8] * r2;
+        elem(0, j) -= s_small[0] * r0 + s_small[1] * r1 + s_small[2] * r2;
+        elem(1, j) -= s_small[3] * r0 + s_small[4] * r1 + s_small[5] * r2;
+        elem(2, j) -= s_small[6] * r0 + s_small[7] * r1 + s_small[8] * r2;
       }
       __syncthreads();
     }
   }
   if (I == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_gj));
-  // rows of Ac^-1 are now sAc[r * 2 nc + nc + j]
-  const double * Ai0 = sAc + nc, * Ai1 = sAc + 2 * nc + nc, * Ai2 = sAc + 4 * nc + nc;
+  // rows of Ac^-1 are now sAr[r * nc + j]
+  __syncthreads();
+  const double * Ai0 = sAr, * Ai1 = sAr + nc, * Ai2 = sAr + 2 * nc;
 
   // ---- CG start: r = b, coarse residual, z = M^-1 r ----
   double accb[1] = {0};
@@ -1089,7 +1097,7 @@ struct b200pg {
   std::vector<int32_t> corr_ids;
   std::vector<double> corr_pose;
   // device
-  DevBuf<int32_t> d_eidx, d_adj_start, d_adj;
+  DevBuf<int32_t> d_eidx, d_adj_start, d_adj, d_agg_start, d_agg_of;
   DevBuf<uint8_t> d_free;
   DevBuf<double> d_gz, d_gp, d_gPt, d_gRow, d_grc, d_e1, d_e2;
   bool debug = false;
@@ -1307,33 +1315,48 @@ static int solve(b200pg * h, b200pg_summary * sum)
     }
   }
   if (h->precond == 1 && !h->force_global_pcg) {
-    // two-level preconditioner: one aggregate per 256-thread CTA; prefer two CTAs per SM (smaller aggregates
-    // -> fewer CG iterations), fall back to one per SM when shared memory does not allow two
-    for (int per_sm = 2; per_sm >= 1 && !L.use_2lvl; --per_sm) {
+    // two-level preconditioner: one aggregate per 256-thread CTA. One CTA per SM is preferred: with two per SM
+    // (295 aggregates at cfg4) CG needs 28 % fewer iterations, but the all-to-all exchanges and the 295-step
+    // Gauss-Jordan get slower (20 us/iteration instead of 12.6; measured 120 ms vs 95 ms). Two per SM is the
+    // fallback when one aggregate per SM does not fit shared memory.
+    for (int per_sm = 1; per_sm <= 2 && !L.use_2lvl; ++per_sm) {
       const int G2 = std::min(per_sm * sms, std::max(1, (N + 15) / 16));
-      const int npc = (N + G2 - 1) / G2;
-      const int Gu = (N + npc - 1) / npc;
-      int max_slots = 1;
+      // contiguous node ranges of equal node count: compact aggregates give the best coarse space (balancing by
+      // block count was tried: it merges sparse chain stretches into large aggregates and costs 60 % more iterations)
+      std::vector<int32_t> agg_start, agg_of(N);
+      {
+        const int per = (N + G2 - 1) / G2;
+        for (int i = 0; i < N; i += per) agg_start.push_back(i);
+        agg_start.push_back(N);
+        for (int a = 0; a + 1 < (int)agg_start.size(); ++a)
+          for (int i = agg_start[a]; i < agg_start[a + 1]; ++i) agg_of[i] = a;
+      }
+      const int Gu = (int)agg_start.size() - 1;
+      int max_slots = 1, npc = 1;
       for (int c = 0; c < Gu; ++c) {
-        const int lo = c * npc, hi = std::min(N, lo + npc);
-        max_slots = std::max(max_slots, adj_start[hi] - adj_start[lo]);
+        max_slots = std::max(max_slots, adj_start[agg_start[c + 1]] - adj_start[agg_start[c]]);
+        npc = std::max(npc, agg_start[c + 1] - agg_start[c]);
       }
       const int nc = 3 * Gu;
-      const size_t bytes2 = ((size_t)max_slots * 12 + (size_t)npc * 36 + (size_t)7 * nc + (size_t)4 * Gu) * sizeof(double) +
+      const int ex_doubles = std::max(4 * Gu, 3 * nc - 3 * max_slots);
+      const size_t bytes2 = ((size_t)max_slots * 12 + (size_t)npc * 36 + (size_t)4 * nc + (size_t)ex_doubles) * sizeof(double) +
                             ((size_t)2 * max_slots + npc + 1) * sizeof(int) + 16;
       if (bytes2 > 220 * 1024) continue;
       int occ = 0;
       B200_CUDA(cudaFuncSetAttribute(k_pg_pcg_2lvl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2));
       B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pg_pcg_2lvl, 256, bytes2));
-      if (h->debug) fprintf(stderr, "[b200pg] two-level plan: %d aggregates of %d nodes, max %d blocks/CTA, %zu B smem, occupancy %d/SM\n", Gu, npc, max_slots, bytes2, occ);
+      if (h->debug) fprintf(stderr, "[b200pg] two-level plan: %d aggregates, <= %d nodes and <= %d blocks each, %zu B smem, occupancy %d/SM\n", Gu, npc, max_slots, bytes2, occ);
       if (occ * sms < Gu) continue;
       L.use_2lvl = true; L.smem2_bytes = bytes2; L.blocks2 = Gu;
       h->d_gz.reserve(n3); h->d_gp.reserve(2 * n3);
       h->d_bar.reserve(std::max<size_t>(4096, (size_t)Gu + 4));
       h->d_gPt.reserve(9 * (size_t)N); h->d_gRow.reserve((size_t)Gu * 6 * nc); h->d_grc.reserve(nc);
       h->d_e1.reserve((size_t)2 * Gu * kSlotStride); h->d_e2.reserve((size_t)2 * Gu * kSlotStride);
+      up(h->d_agg_start, agg_start, st); up(h->d_agg_of, agg_of, st);
+      B200_CUDA(cudaStreamSynchronize(st));   // the two vectors go out of scope
       Pcg2Cfg & c2 = L.cfg2;
-      c2.npc = npc; c2.max_slots = max_slots; c2.gz = h->d_gz.p; c2.gp = h->d_gp.p; c2.gPt = h->d_gPt.p; c2.gRow = h->d_gRow.p;
+      c2.npc = npc; c2.max_slots = max_slots; c2.ex_doubles = ex_doubles; c2.agg_start = h->d_agg_start.p; c2.agg_of = h->d_agg_of.p;
+      c2.gz = h->d_gz.p; c2.gp = h->d_gp.p; c2.gPt = h->d_gPt.p; c2.gRow = h->d_gRow.p;
       c2.grc = h->d_grc.p; c2.e1 = h->d_e1.p; c2.e2 = h->d_e2.p; c2.bar = h->d_bar.p; c2.gjflag = h->d_bar.p + 1;
     }
   }

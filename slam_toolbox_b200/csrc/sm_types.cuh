@@ -2,6 +2,7 @@
 // and sm_sweep.cu (batched loop-closure sweep).
 #pragma once
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -23,6 +24,13 @@ struct GridGeom {
   double scale = 0.0;
   double off_x = 0.0, off_y = 0.0;  // CoordinateConverter offset of the last raster
   std::vector<uint8_t> kernel;
+};
+
+// scratch of the host-side occupancy replay (host_cells)
+struct CellScratch {
+  std::vector<uint64_t> bits;
+  std::vector<uint32_t> touched;
+  std::vector<std::pair<int, int>> foot;
 };
 
 // One CorrelateScan pass prepared on the host (see build_plan)
@@ -179,6 +187,7 @@ struct b200sm {
   b200::DevBuf<int32_t> d_cells, d_offsets, d_sums;
   b200::PinBuf<int32_t> h_stage_i, h_sums;
   bool have_raster = false;
+  b200::CellScratch cell_scratch;
   bool force_generic = false;   // testing: run sweeps on the generic kernel even when the fast path applies
 
   b200::SweepHost sweep;

@@ -144,7 +144,8 @@ int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset);
 /* bytes copied host->device by upload and device->host by fetch since the last reset */
 int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_bytes, int32_t reset);
 /* Tuning / testing switches. "force_generic_sweep" = 1 runs batched sweeps on the generic kernel even
- * where the shared-memory fast path applies (both produce identical results). */
+ * where the shared-memory fast path applies; "no_beam_dedup" = 1 keeps one lookup descriptor per beam in the fast
+ * path instead of merging beams that hit the same cell (all variants produce identical results). */
 int b200sm_set_option(b200sm * h, const char * name, int32_t value);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t b200sm_launch_count(const b200sm * h);
@@ -174,6 +175,10 @@ typedef struct b200pg_opts {
    * normal equations, iterated to ||r|| <= pcg_tolerance * ||b|| */
   double pcg_tolerance;              /* 1e-10 */
   int32_t pcg_max_iterations;        /* 20000 */
+  /* ceres_loss_function (ceres_solver.cpp:82-94): 0 = none (squared loss, the default), 1 = HuberLoss(loss_scale),
+   * 2 = CauchyLoss(loss_scale); the reference uses scale 0.7 for both */
+  int32_t loss_function;
+  double loss_scale;                 /* 0.7 */
 } b200pg_opts;
 
 typedef struct b200pg_summary {

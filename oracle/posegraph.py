@@ -81,6 +81,8 @@ class Options:
     use_nonmonotonic_steps: bool = True
     max_consecutive_nonmonotonic_steps: int = 3
     max_num_consecutive_invalid_steps: int = 3
+    loss_function: str = "none"      # "none" | "huber" | "cauchy"  (solvers/ceres_solver.cpp:82-94)
+    loss_scale: float = 0.7
 
 
 @dataclass
@@ -97,7 +99,8 @@ class Summary:
 class Problem:
     """Vectorised residual / Jacobian of PoseGraph2dErrorTerm over all edges."""
 
-    def __init__(self, poses, edge_a, edge_b, z, U, fixed):
+    def __init__(self, poses, edge_a, edge_b, z, U, fixed, loss="none", loss_scale=0.7):
+        self.loss, self.loss_a = loss, loss_scale
         self.N = len(poses)
         self.ea = np.asarray(edge_a, dtype=np.int64)
         self.eb = np.asarray(edge_b, dtype=np.int64)
@@ -113,7 +116,30 @@ class Problem:
         self.col = -np.ones(self.N, dtype=np.int64)
         self.col[self.free] = np.arange(len(self.free))
 
+    def _rho(self, sq):
+        """ceres::HuberLoss / CauchyLoss Evaluate: rho(s), rho'(s)."""
+        a, b = self.loss_a, self.loss_a ** 2
+        tiny = np.finfo(np.float64).tiny
+        if self.loss == "huber":
+            r = np.sqrt(np.maximum(sq, tiny))
+            big = sq > b
+            return np.where(big, 2 * a * r - b, sq), np.where(big, np.maximum(tiny, a / r), 1.0)
+        if self.loss == "cauchy":
+            s = 1.0 + sq / b
+            return b * np.log(s), np.maximum(tiny, 1.0 / s)
+        return sq, np.ones_like(sq)
+
+    def cost(self, x):
+        r = self.raw_residuals(x).reshape(-1, 3)
+        return 0.5 * float(self._rho((r * r).sum(axis=1))[0].sum())
+
     def residuals(self, x):
+        """Residuals after Ceres' Corrector (rho'' <= 0 for both losses: scale by sqrt(rho'))."""
+        r = self.raw_residuals(x).reshape(-1, 3)
+        w = np.sqrt(self._rho((r * r).sum(axis=1))[1])
+        return (r * w[:, None]).reshape(-1)
+
+    def raw_residuals(self, x):
         pa, pb = x[self.ea], x[self.eb]
         c, s = np.cos(pa[:, 2]), np.sin(pa[:, 2])
         dx, dy = pb[:, 0] - pa[:, 0], pb[:, 1] - pa[:, 1]
@@ -139,6 +165,11 @@ class Problem:
         B[:, 2, 2] = 1.0
         JA = np.einsum("eij,ejk->eik", self.U, A)
         JB = np.einsum("eij,ejk->eik", self.U, B)
+        if self.loss != "none":
+            r = self.raw_residuals(x).reshape(-1, 3)
+            w = np.sqrt(self._rho((r * r).sum(axis=1))[1])
+            JA = JA * w[:, None, None]
+            JB = JB * w[:, None, None]
         rows = (3 * np.arange(E)[:, None, None] + np.arange(3)[None, :, None]) + np.zeros((1, 1, 3), dtype=np.int64)
         ca, cb = self.col[self.ea], self.col[self.eb]
         colsA = 3 * ca[:, None, None] + np.arange(3)[None, None, :] + np.zeros((1, 3, 1), dtype=np.int64)
@@ -170,7 +201,7 @@ def solve(poses, edge_a, edge_b, z, cov=None, U=None, fixed=0, opts: Options | N
     x = np.array(poses, dtype=np.float64)
     if U is None:
         U = np.stack([sqrt_information(c) for c in cov])
-    pb = Problem(x, edge_a, edge_b, z, U, fixed)
+    pb = Problem(x, edge_a, edge_b, z, U, fixed, o.loss_function, o.loss_scale)
     sm = Summary()
     nfree = 3 * len(pb.free)
     if nfree == 0 or len(pb.ea) == 0:
@@ -178,8 +209,7 @@ def solve(poses, edge_a, edge_b, z, cov=None, U=None, fixed=0, opts: Options | N
         return x, sm
 
     def evaluate(xx):
-        r = pb.residuals(xx)
-        return 0.5 * float(r @ r), r
+        return pb.cost(xx), pb.residuals(xx)
 
     def grad_and_jac(xx, r, scale):
         J = pb.jacobian(xx)

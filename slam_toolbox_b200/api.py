@@ -54,7 +54,8 @@ class PgOpts(C.Structure):
                 ("min_trust_region_radius", C.c_double), ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
                 ("jacobi_scaling", C.c_int32), ("use_nonmonotonic_steps", C.c_int32),
                 ("max_consecutive_nonmonotonic_steps", C.c_int32), ("max_num_consecutive_invalid_steps", C.c_int32),
-                ("pcg_tolerance", C.c_double), ("pcg_max_iterations", C.c_int32)]
+                ("pcg_tolerance", C.c_double), ("pcg_max_iterations", C.c_int32),
+                ("loss_function", C.c_int32), ("loss_scale", C.c_double)]
 
 
 class PgSummary(C.Structure):

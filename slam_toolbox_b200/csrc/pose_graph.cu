@@ -58,6 +58,8 @@ struct PgDev {
   double * pr, * pz, * pp0, * pp1, * pq, * Minv;   // PCG work vectors [N][3], Minv [N][6]
   double * partial;         // [kMaxPartials * 4] per-CTA partial sums
   double * scalars;         // small result block
+  int loss;                 // 0 none, 1 Huber, 2 Cauchy (ceres_solver.cpp:82-94)
+  double loss_a;            // loss scale
 };
 
 __device__ __forceinline__ double wrap_angle(double a)   // ceres_utils.h:27-32
@@ -110,6 +112,20 @@ __device__ __forceinline__ void edge_residual(const double * pa, const double * 
   r[2] = U[5] * e2;
 }
 
+// ceres::LossFunction::Evaluate for the two losses the reference offers: rho(s) and rho'(s), s = ||r||^2.
+// Both have rho'' <= 0, for which Ceres' Corrector reduces to scaling residual and Jacobian by sqrt(rho').
+__device__ __forceinline__ void loss_eval(int loss, double a, double s, double & rho, double & rho1)
+{
+  const double b = a * a;
+  if (loss == 1) {          // HuberLoss
+    if (s > b) { const double r = sqrt(s); rho = 2.0 * a * r - b; rho1 = fmax(2.2250738585072014e-308, a / r); }
+    else { rho = s; rho1 = 1.0; }
+  } else if (loss == 2) {   // CauchyLoss
+    const double sum = 1.0 + s / b;
+    rho = b * log(sum); rho1 = fmax(2.2250738585072014e-308, 1.0 / sum);
+  } else { rho = s; rho1 = 1.0; }
+}
+
 // Fused linearisation: residual, Jacobian blocks w.r.t. node a and b (analytic form of the
 // reference's autodiff), Jacobi column scaling, off-diagonal normal block M = A~^T B~, cost partial.
 // mode 0: full linearisation at d.x into d.lin ; mode 1: cost only at d.xc.
@@ -124,8 +140,18 @@ __global__ void __launch_bounds__(kPgThreads) k_pg_linearize(PgDev d, int mode)
     const double * U = d.U + 6 * e;
     double c, s, dx, dy, r[3];
     edge_residual(pa, pb, d.z + 3 * e, U, c, s, dx, dy, r);
-    cost[0] += r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    const double sq = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    double w = 1.0;   // sqrt(rho'): Corrector::CorrectResiduals / CorrectJacobian for rho'' <= 0
+    if (d.loss) {
+      double rho, rho1;
+      loss_eval(d.loss, d.loss_a, sq, rho, rho1);
+      cost[0] += rho;
+      w = sqrt(rho1);
+    } else {
+      cost[0] += sq;
+    }
     if (mode == 1) continue;
+    r[0] *= w; r[1] *= w; r[2] *= w;
     // de/d(xa,ya,tha) and de/d(xb,yb,thb)
     const double Ae[9] = {-c, -s, -s * dx + c * dy, s, -c, -c * dx - s * dy, 0.0, 0.0, -1.0};
     const double Be[9] = {c, s, 0.0, -s, c, 0.0, 0.0, 0.0, 1.0};
@@ -139,7 +165,7 @@ __global__ void __launch_bounds__(kPgThreads) k_pg_linearize(PgDev d, int mode)
       B[3 + j] = U[3] * Be[3 + j] + U[4] * Be[6 + j];
       B[6 + j] = U[5] * Be[6 + j];
     }
-    const double fa = d.is_free[a] ? 1.0 : 0.0, fb = d.is_free[b] ? 1.0 : 0.0;
+    const double fa = d.is_free[a] ? w : 0.0, fb = d.is_free[b] ? w : 0.0;
     const double * sa = d.scale + 3 * a, * sb = d.scale + 3 * b;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -1131,6 +1157,8 @@ void b200pg_defaults(b200pg_opts * o)
   o->max_num_consecutive_invalid_steps = 3;
   o->pcg_tolerance = 1e-10;
   o->pcg_max_iterations = 20000;
+  o->loss_function = 0;
+  o->loss_scale = 0.7;
 }
 
 // karto::Matrix3::Inverse by cofactors (Karto.h:2533-2577) then Eigen's llt().matrixU()
@@ -1287,6 +1315,7 @@ static int solve(b200pg * h, b200pg_summary * sum)
   d.lin = h->d_lin.p; d.Hd = h->d_Hd.p; d.g = h->d_g.p; d.diag = h->d_diag.p; d.y = h->d_y.p; d.pr = h->d_pr.p;
   d.pz = h->d_pz.p; d.pp0 = h->d_pp0.p; d.pp1 = h->d_pp1.p; d.pq = h->d_pq.p; d.Minv = h->d_Minv.p;
   d.partial = h->d_partial.p; d.scalars = h->d_scalars.p;
+  d.loss = o.loss_function; d.loss_a = o.loss_scale;
   int dev = 0, sms = 148, per_sm = 1;
   B200_CUDA(cudaGetDevice(&dev));
   B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1510,7 +1539,8 @@ int b200pg_create(const b200pg_opts * opts, b200pg ** out)
   std::unique_ptr<b200pg> h(new b200pg());
   if (opts) h->o = *opts; else b200pg_defaults(&h->o);
   if (h->o.max_num_iterations < 0 || !(h->o.pcg_tolerance > 0) || h->o.pcg_max_iterations <= 0 ||
-      !(h->o.initial_trust_region_radius > 0)) {
+      !(h->o.initial_trust_region_radius > 0) || h->o.loss_function < 0 || h->o.loss_function > 2 ||
+      (h->o.loss_function != 0 && !(h->o.loss_scale > 0))) {
     set_last_error("b200pg_create: invalid options");
     return B200_ERR_INVALID_ARG;
   }

@@ -756,6 +756,7 @@ int b200sm_set_option(b200sm * h, const char * name, int32_t value)
 {
   if (!h || !name) return B200_ERR_INVALID_ARG;
   if (std::string(name) == "force_generic_sweep") { h->force_generic = value != 0; return B200_OK; }
+  if (std::string(name) == "no_beam_dedup") { h->no_dedup = value != 0; return B200_OK; }
   set_last_error(std::string("unknown option ") + name);
   return B200_ERR_INVALID_ARG;
 }

@@ -448,15 +448,17 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
       // ---- FAST beams ----
       for (int wi = warp; wi < nA * f.xtiles; wi += nwarps) {
         const int a = wi / f.xtiles, xt = wi - a * f.xtiles;
-        const int32_t * cs = f.cls_start + ((size_t)q * nA + a) * 17 + ph * 4;
+        const int32_t * cs = f.cls_start + ((size_t)q * nA + a) * 33 + ph * 8;
         const uint32_t base = (uint32_t)((y_l * kSubPitchW + 4 * xt + j_l) * 4);
         int32_t * Arow = A + a * P;
         for (int m = 0; m < 4; ++m) {
-          int b = cs[m];
-          const int e = cs[m + 1];
+          // group layout: [plain entries (one per beam) | multi entries (descriptor + multiplicity >= 3)]
+          int b = cs[2 * m];
+          const int mb = cs[2 * m + 1], me = cs[2 * m + 2];
+          bool multi_done = (mb == me);
           const int x0 = 4 * (4 * xt + j_l) - m;
-          while (b < e) {
-            const int ce = min(e, b + kFastChunk);
+          do {
+            const int ce = min(mb, b + kFastChunk);
             uint32_t T0[kFastRowTiles], T1[kFastRowTiles];
 #pragma unroll
             for (int r = 0; r < kFastRowTiles; ++r) { T0[r] = 0; T1[r] = 0; }
@@ -499,6 +501,26 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
               }
             }
             b = ce;
+            if (b == mb && !multi_done) {
+              // beams that share one grid cell (several per 5 cm cell at indoor ranges): one load, fields times k.
+              // The host only builds multi entries when the whole group's weight fits one flush (<= kFastChunk).
+              for (int b0 = mb; b0 < me; b0 += 32) {
+                const int cnt = min(32, me - b0);
+                const uint32_t mine = (lane < cnt) ? 4u * f.beams[b0 + lane] : 0u;
+                const uint32_t myk = (lane < cnt) ? f.mult[b0 + lane] : 0u;
+                for (int k = 0; k < cnt; ++k) {
+                  const uint32_t o0 = base + __shfl_sync(0xffffffffu, mine, k);
+                  const uint32_t kk = __shfl_sync(0xffffffffu, myk, k);
+#pragma unroll
+                  for (int r = 0; r < kFastRowTiles; ++r) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * kPitchB);
+                    T0[r] += even_bytes(w) * kk;
+                    T1[r] += odd_bytes(w) * kk;
+                  }
+                }
+              }
+              multi_done = true;
+            }
             // flush the 16-bit fields: pose x = x0 + t, t = 0..3 (most windows of a sparse grid are empty)
             uint32_t any = 0;
 #pragma unroll
@@ -515,7 +537,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
               if (v2 && (unsigned)(x0 + 2) < (unsigned)nX) atomicAdd(dst + 2, v2);
               if (v3 && (unsigned)(x0 + 3) < (unsigned)nX) atomicAdd(dst + 3, v3);
             }
-          }
+          } while (b < mb || !multi_done);
         }
       }
       // ---- SLOW beams: the reference's rule on the linear index (M.cpp:1192-1200), this phase's cells only ----
@@ -812,9 +834,10 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   const size_t smem = (size_t)sub_rows * kSubPitchW * 4 + (size_t)nA * nX * nY * 4;
   if (smem > 227 * 1024 - 1024) return false;
   if ((size_t)5 * nX * nY * sizeof(double) > (size_t)sub_rows * kSubPitchW * 4) return false;   // epilogue scratch reuses S
-  std::vector<int32_t> origin(2 * (size_t)nq), cls_start((size_t)nq * nA * 17), slow, slow_start((size_t)nq * (nA + 1));
-  std::vector<uint16_t> beams;
+  std::vector<int32_t> origin(2 * (size_t)nq), cls_start((size_t)nq * nA * 33), slow, slow_start((size_t)nq * (nA + 1));
+  std::vector<uint16_t> beams, mult;
   beams.reserve((size_t)nq * nA * n);
+  mult.reserve((size_t)nq * nA * n);
   for (int q = 0; q < nq; ++q) {
     const CorrPlan & pl = S.plans[q];
     for (int k = 1; k < nX; ++k) if (pl.xs[k] != pl.xs[0] + 2 * k) return false;   // coarse step must be exactly 2 cells
@@ -840,13 +863,30 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
           if (dv != kDevInvalid) slow.push_back(dv);   // can still index [0, data_size) for some pose
         }
       }
-      int32_t * cs = &cls_start[((size_t)q * nA + a) * 17];
+      int32_t * cs = &cls_start[((size_t)q * nA + a) * 33];
       for (int k = 0; k < 16; ++k) {
-        cs[k] = (int32_t)beams.size();
-        std::sort(group[k].begin(), group[k].end());
-        beams.insert(beams.end(), group[k].begin(), group[k].end());
+        std::vector<uint16_t> & gk = group[k];
+        std::sort(gk.begin(), gk.end());
+        cs[2 * k] = (int32_t)beams.size();
+        // run-length encode: beams that land in the same cell share a descriptor. Entries with multiplicity >= 3
+        // go to the group's multi list (one load, fields multiplied), provided the whole group fits one flush.
+        const bool dedup = !h->no_dedup && gk.size() <= (size_t)kFastChunk;
+        std::vector<std::pair<uint16_t, uint16_t>> multi;
+        for (size_t i = 0; i < gk.size();) {
+          size_t j = i;
+          while (j < gk.size() && gk[j] == gk[i]) ++j;
+          const size_t cnt = j - i;
+          if (dedup && cnt >= 3) {
+            multi.emplace_back(gk[i], (uint16_t)cnt);
+          } else {
+            for (size_t t = 0; t < cnt; ++t) { beams.push_back(gk[i]); mult.push_back(1); }
+          }
+          i = j;
+        }
+        cs[2 * k + 1] = (int32_t)beams.size();
+        for (auto & mk : multi) { beams.push_back(mk.first); mult.push_back(mk.second); }
       }
-      cs[16] = (int32_t)beams.size();
+      cs[32] = (int32_t)beams.size();
     }
     slow_start[(size_t)q * (nA + 1) + nA] = (int32_t)slow.size();
   }
@@ -855,7 +895,9 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   h2d(S.d_fast_cls, cls_start.data(), cls_start.size(), st);
   S.d_fast_beams.reserve(std::max<size_t>(beams.size(), 1) + 8);
   if (!beams.empty()) B200_CUDA(cudaMemcpyAsync(S.d_fast_beams.p, beams.data(), beams.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-  S.h2d_bytes += (int64_t)(beams.size() * sizeof(uint16_t));
+  S.d_fast_mult.reserve(std::max<size_t>(mult.size(), 1) + 8);
+  if (!mult.empty()) B200_CUDA(cudaMemcpyAsync(S.d_fast_mult.p, mult.data(), mult.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  S.h2d_bytes += (int64_t)(2 * beams.size() * sizeof(uint16_t));
   slow.push_back(0);
   h2d(S.d_fast_slow, slow.data(), slow.size(), st);
   h2d(S.d_fast_slow_start, slow_start.data(), slow_start.size(), st);
@@ -865,6 +907,7 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   S.fast.xtiles = xtiles;
   S.fast.origin = S.d_fast_origin.p;
   S.fast.beams = S.d_fast_beams.p;
+  S.fast.mult = S.d_fast_mult.p;
   S.fast.cls_start = S.d_fast_cls.p;
   S.fast.slow = S.d_fast_slow.p;
   S.fast.slow_start = S.d_fast_slow_start.p;

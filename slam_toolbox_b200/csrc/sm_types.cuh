@@ -129,8 +129,9 @@ struct FastDev {
   int sub_rows;                  // allocated sub-grid rows (incl. padding rows)
   int xtiles;                    // ceil((nX + 3) / 16)
   const int32_t * origin;        // [nq][2]  grid column / row of pose (0, 0)
-  const uint16_t * beams;        // FAST descriptors, grouped
-  const int32_t * cls_start;     // [nq][nA][17] group boundaries into beams (group = phase * 4 + m)
+  const uint16_t * beams;        // FAST descriptors, grouped; per group: plain entries, then multi entries
+  const uint16_t * mult;         // multiplicity of every entry (1 for plain entries)
+  const int32_t * cls_start;     // [nq][nA][33]: group g = phase * 4 + m -> [2g] plain begin, [2g+1] multi begin, [2g+2] end
   const int32_t * slow;          // SLOW beams: device-form linear offsets
   const int32_t * slow_start;    // [nq][nA + 1]
 };
@@ -156,7 +157,7 @@ struct SweepHost {
     d_cells, d_cell_count, d_ws_sums, d_fine_off, d_fine_pos, d_fine_sums;
   DevBuf<double> d_qgeom, d_center, d_qd, d_angpen, d_points, d_ws_probs;
   DevBuf<uint8_t> d_ws_grid, d_kernel;
-  DevBuf<uint16_t> d_fast_beams;
+  DevBuf<uint16_t> d_fast_beams, d_fast_mult;
   DevBuf<int32_t> d_fast_origin, d_fast_cls, d_fast_slow, d_fast_slow_start;
   FastDev fast{};
   size_t fast_smem = 0;
@@ -188,6 +189,7 @@ struct b200sm {
   b200::PinBuf<int32_t> h_stage_i, h_sums;
   bool have_raster = false;
   b200::CellScratch cell_scratch;
+  bool no_dedup = false;        // testing: keep one descriptor per beam in the fast sweep lists
   bool force_generic = false;   // testing: run sweeps on the generic kernel even when the fast path applies
 
   b200::SweepHost sweep;

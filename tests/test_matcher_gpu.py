@@ -174,6 +174,11 @@ def test_fast_and_generic_sweep_kernels_agree_with_the_oracle(grid):
     exp = [pm.match(pq[q], pc[sw.chain_start[c]:sw.chain_start[c + 1]], False, False) for q in range(2) for c in range(10)]
     fast = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
     fast_best = gm.batch_best()
+    gm.set_option("no_beam_dedup", 1)          # one descriptor per beam instead of (descriptor, multiplicity)
+    plain = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
+    for a, b in zip(fast, plain):
+        assert np.array_equal(a, b)
+    gm.set_option("no_beam_dedup", 0)
     gm.set_option("force_generic_sweep", 1)
     gen = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
     gen_best = gm.batch_best()

@@ -136,3 +136,29 @@ def test_two_level_and_jacobi_preconditioners_agree(monkeypatch):
     dxy, dth = diff(s1.GetCorrections()[1], s2.GetCorrections()[1])
     assert dxy < 1e-7 and dth < 1e-8, (dxy, dth)
     assert s1.summary.pcg_iterations < 0.6 * s2.summary.pcg_iterations, (s1.summary.pcg_iterations, s2.summary.pcg_iterations)
+
+
+@pytest.mark.parametrize("loss,code", [("huber", 1), ("cauchy", 2)])
+def test_robust_losses_match_oracle_and_reject_outliers(loss, code):
+    """ceres_loss_function = HuberLoss / CauchyLoss (scale 0.7, solvers/ceres_solver.cpp:82-94) with gross outliers
+    injected into some loop-closure edges."""
+    g = synth.make_pose_graph(21, 2500, 9000, sigma_xy=0.03, sigma_th=0.01)
+    rng = np.random.default_rng(0)
+    z = g["z"].copy()
+    loops = np.arange(2499, len(z))
+    bad = rng.choice(loops, size=max(4, len(loops) // 50), replace=False)
+    z[bad, :2] += rng.normal(0, 2.0, (len(bad), 2))
+    g = dict(g, z=z)
+    xo, so = PG.solve(g["init"], g["edge_a"], g["edge_b"], g["z"], cov=g["cov"], opts=PG.Options(loss_function=loss))
+    s = build(g, loss_function=code, loss_scale=0.7)
+    assert s.Compute()
+    dxy, dth = diff(s.GetCorrections()[1], xo)
+    assert dxy < TOL_XY and dth < TOL_TH, (dxy, dth)
+    assert s.summary.iterations == so.iterations
+    assert abs(s.summary.final_cost - so.final_cost) <= 1e-8 * so.final_cost
+    # the robust solution is closer to the truth than the squared-loss one
+    s0 = build(g)
+    assert s0.Compute()
+    e_rob = np.abs(s.GetCorrections()[1][:, :2] - g["truth"][:, :2]).max()
+    e_sq = np.abs(s0.GetCorrections()[1][:, :2] - g["truth"][:, :2]).max()
+    assert e_rob < e_sq

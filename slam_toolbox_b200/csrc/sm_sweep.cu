@@ -653,6 +653,32 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   cudaStream_t st = h->stream;
   const GridGeom & g0 = h->g;
 
+  // ---- candidate scans first: their 17 KB/scan copy runs while the host builds the per-query tables ----
+  std::vector<int32_t> pt_start(nscans + 1, 0);
+  int max_n = 0;
+  bool contiguous = true;
+  for (int s = 0; s < nscans; ++s) {
+    if (scans[s].n < 0 || (scans[s].n > 0 && !scans[s].points_xy)) { set_last_error("sweep: candidate scan without points"); return B200_ERR_INVALID_ARG; }
+    pt_start[s + 1] = pt_start[s] + scans[s].n;
+    max_n = std::max(max_n, scans[s].n);
+    if (s > 0 && scans[s].points_xy != scans[s - 1].points_xy + 2 * (size_t)scans[s - 1].n) contiguous = false;
+  }
+  const size_t npts = (size_t)pt_start[nscans];
+  S.d_points.reserve(2 * npts + 2);
+  if (contiguous) {
+    // caller laid the scans out back to back (pinned or not): one copy straight from its buffer
+    B200_CUDA(cudaMemcpyAsync(S.d_points.p, scans[0].points_xy, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    S.h2d_bytes += (int64_t)(2 * npts * sizeof(double));
+  } else {
+    S.h_d.reserve(2 * npts);
+    for (int s = 0; s < nscans; ++s)
+      std::memcpy(S.h_d.p + 2 * (size_t)pt_start[s], scans[s].points_xy, 2 * (size_t)scans[s].n * sizeof(double));
+    B200_CUDA(cudaMemcpyAsync(S.d_points.p, S.h_d.p, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, st));
+    S.h2d_bytes += (int64_t)(2 * npts * sizeof(double));
+    B200_CUDA(cudaStreamSynchronize(st));   // h_d is reused for the per-query tables below
+  }
+  S.max_n = std::max(max_n, 1);
+
   // ---- coarse plans, one per query ----
   double off[2], res[2];
   coarse_search(h, off, res);
@@ -712,31 +738,6 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
     h2d(S.d_qd, S.h_d.p, per * nq, st);
   }
   B200_CUDA(cudaStreamSynchronize(st));   // h_i / h_d are reused below
-
-  // ---- candidate scans ----
-  std::vector<int32_t> pt_start(nscans + 1, 0);
-  int max_n = 0;
-  bool contiguous = true;
-  for (int s = 0; s < nscans; ++s) {
-    if (scans[s].n < 0 || (scans[s].n > 0 && !scans[s].points_xy)) { set_last_error("sweep: candidate scan without points"); return B200_ERR_INVALID_ARG; }
-    pt_start[s + 1] = pt_start[s] + scans[s].n;
-    max_n = std::max(max_n, scans[s].n);
-    if (s > 0 && scans[s].points_xy != scans[s - 1].points_xy + 2 * (size_t)scans[s - 1].n) contiguous = false;
-  }
-  const size_t npts = (size_t)pt_start[nscans];
-  S.d_points.reserve(2 * npts + 2);
-  if (contiguous) {
-    // caller laid the scans out back to back (pinned or not): one copy straight from its buffer
-    B200_CUDA(cudaMemcpyAsync(S.d_points.p, scans[0].points_xy, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, st));
-    S.h2d_bytes += (int64_t)(2 * npts * sizeof(double));
-  } else {
-    S.h_d.reserve(2 * npts);
-    for (int s = 0; s < nscans; ++s)
-      std::memcpy(S.h_d.p + 2 * (size_t)pt_start[s], scans[s].points_xy, 2 * (size_t)scans[s].n * sizeof(double));
-    B200_CUDA(cudaMemcpyAsync(S.d_points.p, S.h_d.p, 2 * npts * sizeof(double), cudaMemcpyHostToDevice, st));
-    S.h2d_bytes += (int64_t)(2 * npts * sizeof(double));
-  }
-  S.max_n = std::max(max_n, 1);
 
   // ---- pairs and items ----
   std::vector<int32_t> pair_item_start(npairs + 1, 0);

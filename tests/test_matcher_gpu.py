@@ -188,3 +188,35 @@ def test_fast_and_generic_sweep_kernels_agree_with_the_oracle(grid):
         assert np.array_equal(a, b)
     assert np.array_equal(fast[0], np.array([e[0] for e in exp]))
     assert np.array_equal(fast[1], np.array([e[1] for e in exp])) and np.array_equal(fast[2], np.array([e[2] for e in exp]))
+
+
+def test_sharded_sweep_keys_equal_the_unsharded_reduction():
+    """cfg5 shape at small size: Q queries x C candidate chains, candidates sharded over "ranks" (here: two handles on one
+    GPU, the reduction done with torch.maximum exactly as all_reduce(MAX) would). The per-query winner must not depend on
+    the sharding: highest integer sum, ties to the lowest global candidate id."""
+    import torch
+    from slam_toolbox_b200 import sweep
+    Q, Cn = 4, 48
+    sw = synth.make_loop_sweep(41, n_queries=Q, n_chains=Cn, chain_len=1)
+    gq = H.gpu_block(sw.query_ranges, sw.query_poses)
+
+    def keys_for(lo, hi, offset):
+        gm = H.gpu_matcher(H.MAPPER_LOOP, H.GRID_LOOP)
+        gc = H.gpu_block(sw.cand_ranges[lo:hi], sw.cand_poses[lo:hi])
+        gm.batch_upload(gq, gc, np.arange(hi - lo + 1, dtype=np.int32), None, False)
+        gm.batch_run()
+        k = torch.zeros(Q, dtype=torch.int64, device="cuda")
+        gm.batch_reduce_keys(k.data_ptr(), offset)
+        torch.cuda.synchronize()
+        sums, _, _ = gm.batch_best()
+        return k, sums.reshape(Q, hi - lo)
+
+    full, sums = keys_for(0, Cn, 0)
+    parts = []
+    for r in range(3):
+        lo, hi = sweep.shard_range(Cn, 3, r)
+        parts.append(keys_for(lo, hi, lo)[0])
+    merged = torch.maximum(torch.maximum(parts[0], parts[1]), parts[2])
+    assert torch.equal(merged, full)
+    s, g = sweep.unpack_keys(full.cpu().numpy())
+    assert np.array_equal(s, sums.max(axis=1)) and np.array_equal(g, sums.argmax(axis=1))

@@ -141,6 +141,9 @@ int b200sm_batch_best(b200sm * h, int32_t * best_sum, int32_t * best_index, int3
  * caller hands to ncclAllReduce(ncclMax) / torch.distributed.all_reduce(MAX) next), on the
  * handle's stream. A max over ranks selects the highest sum, ties to the lowest global id. */
 int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset);
+/* Which kernel the uploaded sweep will run on and how its lookups were classified: info = {fast path (1) or generic (0),
+ * FAST descriptors, EDGE beams (window leaves the grid), FAR beams (column offset >= one stride), reason code when the fast path was refused (0 = n/a), CTAs, pairs, items}. */
+int b200sm_batch_info(b200sm * h, int32_t info[8]);
 /* bytes copied host->device by upload and device->host by fetch since the last reset */
 int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_bytes, int32_t reset);
 /* Tuning / testing switches. "force_generic_sweep" = 1 runs batched sweeps on the generic kernel even

@@ -97,6 +97,7 @@ def lib():
     L.b200sm_batch_fetch.argtypes = [C.c_void_p, _DP, _DP, _DP]
     L.b200sm_batch_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.b200sm_batch_best.argtypes = [C.c_void_p, _IP, _IP, _IP]
+    L.b200sm_batch_info.argtypes = [C.c_void_p, _IP]
     L.b200sm_batch_reduce_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.b200sm_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]
     L.b200sm_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
@@ -327,6 +328,12 @@ class ScanMatcher:
     def batch_reduce_keys(self, device_ptr: int, id_offset: int = 0):
         """Per-query packed best-response keys into a device buffer (see b200sm_batch_reduce_keys)."""
         _check(lib().b200sm_batch_reduce_keys(self._h, C.c_void_p(device_ptr), int(id_offset)))
+
+    def batch_info(self):
+        info = np.zeros(8, dtype=np.int32)
+        _check(lib().b200sm_batch_info(self._h, _ip(info)))
+        return dict(fast=bool(info[0]), fast_descriptors=int(info[1]), edge_beams=int(info[2]), far_beams=int(info[3]),
+                    refused_reason=int(info[4]), ctas=int(info[5]), pairs=int(info[6]), items=int(info[7]))
 
     def transfer_bytes(self, reset: bool = False):
         a, b = C.c_int64(), C.c_int64()

@@ -540,7 +540,51 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
           } while (b < mb || !multi_done);
         }
       }
-      // ---- SLOW beams: the reference's rule on the linear index (M.cpp:1192-1200), this phase's cells only ----
+      // ---- EDGE beams: the window leaves the grid (readings close to / beyond the range threshold).
+      //   primary list (this phase = the beam's own parity): poses whose column stays inside [0, stride); rows outside
+      //     [0, height) index outside [0, data_size) in the reference and contribute 0;
+      //   secondary list (row parity flipped): poses whose column left [0, stride) by less than one stride -- the
+      //     reference's linear index (M.cpp:1192-1200) makes them read the neighbouring row at column -/+ stride.
+      //   One thread per (beam, pose), no division. ----
+      {
+        if (f.clip_start[((size_t)q * nA + nA - 1) * 4 + 4] - f.clip_start[(size_t)q * nA * 4] > 0) {
+          const int32_t * cl = f.clip_start + ((size_t)q * nA) * 4 + ph;
+          for (int a = 0; a < nA; ++a) {
+            const int sb = cl[4 * a], se = cl[4 * a + 1];
+            const int work = (se - sb) * P;
+            for (int t = threadIdx.x; t < work; t += blockDim.x) {
+              const int bi = t / P, p = t - bi * P;
+              const int32_t e = f.clip[sb + bi];
+              const int Xb = (int)(int16_t)(e & 0xFFFF), Yb = e >> 16;
+              const int row = Yb + 2 * (p / nX), col = Xb + 2 * (p % nX);
+              if ((unsigned)col >= (unsigned)d.stride || (unsigned)row >= (unsigned)d.height) continue;
+              const int v = S8[(row >> 1) * kPitchB + (col >> 1)];
+              if (v) atomicAdd(A + a * P + p, v);
+            }
+          }
+        }
+        if (f.wrap2_start[((size_t)q * nA + nA - 1) * 4 + 4] - f.wrap2_start[(size_t)q * nA * 4] > 0) {
+          const int32_t * cl = f.wrap2_start + ((size_t)q * nA) * 4 + ph;
+          for (int a = 0; a < nA; ++a) {
+            const int sb = cl[4 * a], se = cl[4 * a + 1];
+            const int work = (se - sb) * P;
+            for (int t = threadIdx.x; t < work; t += blockDim.x) {
+              const int bi = t / P, p = t - bi * P;
+              const int32_t e = f.wrap2[sb + bi];
+              const int Xb = (int)(int16_t)(e & 0xFFFF), Yb = e >> 16;
+              const int col = Xb + 2 * (p % nX);
+              if ((unsigned)col < (unsigned)d.stride) continue;
+              const int r2 = Yb + 2 * (p / nX) + (col < 0 ? -1 : 1);
+              const int c2 = col + (col < 0 ? d.stride : -d.stride);
+              if ((unsigned)r2 >= (unsigned)d.height) continue;
+              const int v = S8[(r2 >> 1) * kPitchB + (c2 >> 1)];
+              if (v) atomicAdd(A + a * P + p, v);
+            }
+          }
+        }
+      }
+      // ---- FAR beams: column offsets of a stride or more (readings near the laser's maximum range at fine grids):
+      //      pose by pose on the linear index with a division, every phase. Rare. ----
       {
         const int32_t * ss = f.slow_start + (size_t)q * (nA + 1);
         const int nslow = ss[nA] - ss[0];
@@ -789,7 +833,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   S.h_out.reserve(npairs);
 
   SweepDev & d = S.dev;
-  d.stride = g0.stride; d.roi_x = g0.roi_x; d.roi_y = g0.roi_y; d.roi_w = g0.roi_w; d.roi_h = g0.roi_h;
+  d.stride = g0.stride; d.height = g0.height; d.roi_x = g0.roi_x; d.roi_y = g0.roi_y; d.roi_w = g0.roi_w; d.roi_h = g0.roi_h;
   d.data_size = g0.data_size; d.ksize = g0.ksize; d.order_dependent = g0.order_dependent ? 1 : 0;
   d.scale = g0.scale; d.kern = S.d_kernel.p;
   d.nX = nX; d.nY = nY; d.nA = nA; d.n = n;
@@ -827,27 +871,35 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   const CorrPlan & p0 = S.plans[0];
   const int nX = p0.nX, nY = p0.nY, nA = p0.nA, n = p0.n, nq = S.nq;
   S.fast.enabled = 0;
-  if (g.order_dependent) return false;
-  if (nY > 8 * kFastRowTiles || (g.stride & 1)) return false;
-  if (g.stride / 2 > kSubPitchW * 4 - 16) return false;   // sub-grid row + the 3-word overhang must fit the pitch
+  S.fast_info[0] = 0; S.fast_info[1] = S.fast_info[2] = S.fast_info[3] = 0;
+  auto bail = [&](int why) { S.fast_info[4] = why; return false; };
+  if (g.order_dependent) return bail(1);
+  if (nY > 8 * kFastRowTiles || (g.stride & 1)) return bail(2);
+  if (g.stride / 2 > kSubPitchW * 4 - 16) return bail(3);   // sub-grid row + the 3-word overhang must fit the pitch
   const int xtiles = (nX + 3 + 15) / 16;
-  const int sub_rows = (g.height + 1) / 2 + 8;               // + padding rows read by idle row tiles
+  int sub_rows = (g.height + 1) / 2 + 8;                     // + padding rows read by idle row tiles
+  // the S region doubles as the FP64 scratch of the reduction (5 P doubles): small grids get extra rows for it
+  sub_rows = std::max(sub_rows, (int)(((size_t)5 * nX * nY * sizeof(double) + kSubPitchW * 4 - 1) / (kSubPitchW * 4)));
   const size_t smem = (size_t)sub_rows * kSubPitchW * 4 + (size_t)nA * nX * nY * 4;
-  if (smem > 227 * 1024 - 1024) return false;
-  if ((size_t)5 * nX * nY * sizeof(double) > (size_t)sub_rows * kSubPitchW * 4) return false;   // epilogue scratch reuses S
+  if (smem > 227 * 1024 - 1024) return bail(4);
+  if ((size_t)5 * nX * nY * sizeof(double) > (size_t)sub_rows * kSubPitchW * 4) return bail(5);   // epilogue scratch reuses S
   std::vector<int32_t> origin(2 * (size_t)nq), cls_start((size_t)nq * nA * 33), slow, slow_start((size_t)nq * (nA + 1));
   std::vector<uint16_t> beams, mult;
+  std::vector<int32_t> clip, clip_start((size_t)nq * nA * 4 + 1), wrap2, wrap2_start((size_t)nq * nA * 4 + 1);
   beams.reserve((size_t)nq * nA * n);
   mult.reserve((size_t)nq * nA * n);
   for (int q = 0; q < nq; ++q) {
     const CorrPlan & pl = S.plans[q];
-    for (int k = 1; k < nX; ++k) if (pl.xs[k] != pl.xs[0] + 2 * k) return false;   // coarse step must be exactly 2 cells
-    for (int k = 1; k < nY; ++k) if (pl.ys[k] != pl.ys[0] + 2 * k) return false;
+    for (int k = 1; k < nX; ++k) if (pl.xs[k] != pl.xs[0] + 2 * k) return bail(6);   // coarse step must be exactly 2 cells
+    for (int k = 1; k < nY; ++k) if (pl.ys[k] != pl.ys[0] + 2 * k) return bail(7);
     const int X0 = pl.xs[0], Y0 = pl.ys[0];
     origin[2 * q] = X0; origin[2 * q + 1] = Y0;
     std::vector<uint16_t> group[16];
+    std::vector<int32_t> cgroup[4], wgroup[4];
     for (int a = 0; a < nA; ++a) {
       for (auto & v : group) v.clear();
+      for (auto & v : cgroup) v.clear();
+      for (auto & v : wgroup) v.clear();
       slow_start[(size_t)q * (nA + 1) + a] = (int32_t)slow.size();
       for (int i = 0; i < n; ++i) {
         const int32_t off = pl.offsets[(size_t)a * n + i];
@@ -859,10 +911,25 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
           const int pp = Xb & 1, pq = Yb & 1, c = Xb >> 1, r = Yb >> 1;
           const int wo = r * kSubPitchW + (c >> 2);
           group[(pq * 2 + pp) * 4 + (c & 3)].push_back((uint16_t)wo);
+        } else if (Xb >= -g.stride && Xb + 2 * (nX - 1) < 2 * g.stride && Xb > -32768 && Xb < 32767 && Yb > -32768 && Yb < 32767) {
+          // EDGE beam: at most one row wrap. Primary entry in the beam's own phase; if some column leaves
+          // [0, stride), a secondary entry in the phase with the row parity flipped.
+          const int32_t e = (int32_t)((uint32_t)(Xb & 0xFFFF) | ((uint32_t)Yb << 16));
+          const bool rows_hit = Yb + 2 * (nY - 1) >= 0 && Yb < g.height;
+          const bool cols_hit = Xb + 2 * (nX - 1) >= 0 && Xb < g.stride;
+          if (rows_hit && cols_hit) cgroup[(Yb & 1) * 2 + (Xb & 1)].push_back(e);
+          const bool wraps = Xb < 0 || Xb + 2 * (nX - 1) >= g.stride;
+          if (wraps && Yb + 2 * (nY - 1) + 1 >= 0 && Yb - 1 < g.height) wgroup[((Yb & 1) ^ 1) * 2 + (Xb & 1)].push_back(e);
         } else {
           const int32_t dv = device_offset(off, g.data_size);
-          if (dv != kDevInvalid) slow.push_back(dv);   // can still index [0, data_size) for some pose
+          if (dv != kDevInvalid) slow.push_back(dv);   // FAR: can still index [0, data_size) for some pose
         }
+      }
+      for (int k = 0; k < 4; ++k) {
+        clip_start[((size_t)q * nA + a) * 4 + k] = (int32_t)clip.size();
+        clip.insert(clip.end(), cgroup[k].begin(), cgroup[k].end());
+        wrap2_start[((size_t)q * nA + a) * 4 + k] = (int32_t)wrap2.size();
+        wrap2.insert(wrap2.end(), wgroup[k].begin(), wgroup[k].end());
       }
       int32_t * cs = &cls_start[((size_t)q * nA + a) * 33];
       for (int k = 0; k < 16; ++k) {
@@ -891,6 +958,8 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
     }
     slow_start[(size_t)q * (nA + 1) + nA] = (int32_t)slow.size();
   }
+  clip_start[(size_t)nq * nA * 4] = (int32_t)clip.size();
+  wrap2_start[(size_t)nq * nA * 4] = (int32_t)wrap2.size();
   // slow_start must be relative to one array: it is (single vector `slow`)
   h2d(S.d_fast_origin, origin.data(), origin.size(), st);
   h2d(S.d_fast_cls, cls_start.data(), cls_start.size(), st);
@@ -900,10 +969,17 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   if (!mult.empty()) B200_CUDA(cudaMemcpyAsync(S.d_fast_mult.p, mult.data(), mult.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
   S.h2d_bytes += (int64_t)(2 * beams.size() * sizeof(uint16_t));
   slow.push_back(0);
+  clip.push_back(0);
+  wrap2.push_back(0);
+  h2d(S.d_fast_clip, clip.data(), clip.size(), st);
+  h2d(S.d_fast_clip_start, clip_start.data(), clip_start.size(), st);
+  h2d(S.d_fast_wrap2, wrap2.data(), wrap2.size(), st);
+  h2d(S.d_fast_wrap2_start, wrap2_start.data(), wrap2_start.size(), st);
   h2d(S.d_fast_slow, slow.data(), slow.size(), st);
   h2d(S.d_fast_slow_start, slow_start.data(), slow_start.size(), st);
   B200_CUDA(cudaStreamSynchronize(st));   // the vectors above go out of scope
   S.fast.enabled = 1;
+  S.fast_info[0] = 1; S.fast_info[1] = (int32_t)beams.size(); S.fast_info[2] = (int32_t)clip.size() - 1; S.fast_info[3] = (int32_t)slow.size() - 1; S.fast_info[4] = 0;
   S.fast.sub_rows = sub_rows;
   S.fast.xtiles = xtiles;
   S.fast.origin = S.d_fast_origin.p;
@@ -911,6 +987,10 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   S.fast.mult = S.d_fast_mult.p;
   S.fast.cls_start = S.d_fast_cls.p;
   S.fast.slow = S.d_fast_slow.p;
+  S.fast.clip = S.d_fast_clip.p;
+  S.fast.clip_start = S.d_fast_clip_start.p;
+  S.fast.wrap2 = S.d_fast_wrap2.p;
+  S.fast.wrap2_start = S.d_fast_wrap2_start.p;
   S.fast.slow_start = S.d_fast_slow_start.p;
   S.fast_smem = smem;
   {
@@ -1124,6 +1204,16 @@ int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset)
   h->launches++;
   return B200_OK;
   B200_GUARD_END
+}
+
+int b200sm_batch_info(b200sm * h, int32_t info[8])
+{
+  if (!h || !info || !h->sweep.uploaded) return B200_ERR_INVALID_ARG;
+  for (int i = 0; i < 5; ++i) info[i] = h->sweep.fast_info[i];
+  info[0] = (h->sweep.fast.enabled && !h->force_generic) ? 1 : 0;
+  info[5] = h->sweep.fast.enabled ? h->sweep.fast_blocks : h->sweep.blocks;
+  info[6] = h->sweep.npairs; info[7] = h->sweep.nitems;
+  return B200_OK;
 }
 
 int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_bytes, int32_t reset)

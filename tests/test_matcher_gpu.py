@@ -140,6 +140,7 @@ def test_full_size_sweep_properties():
     gm = H.gpu_matcher(H.MAPPER_LOOP, H.GRID_LOOP)
     gc, gq = H.gpu_block(sw.cand_ranges, sw.cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
     r1, m1, c1 = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
+    assert gm.batch_info()["fast"]
     gm.batch_upload(gq, gc, sw.chain_start, None, False)
     gm.batch_run(); gm.batch_run()
     r2, m2, c2 = gm.batch_fetch()
@@ -173,6 +174,10 @@ def test_fast_and_generic_sweep_kernels_agree_with_the_oracle(grid):
     gc, gq = H.gpu_block(sw.cand_ranges, sw.cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
     exp = [pm.match(pq[q], pc[sw.chain_start[c]:sw.chain_start[c + 1]], False, False) for q in range(2) for c in range(10)]
     fast = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
+    info = gm.batch_info()
+    assert info["fast"] and info["fast_descriptors"] > 0 and info["edge_beams"] >= 0, info      # the fast path really ran
+    if grid[3] < 12.0:
+        assert info["edge_beams"] > 0, info    # short range threshold: windows that leave the grid are exercised
     fast_best = gm.batch_best()
     gm.set_option("no_beam_dedup", 1)          # one descriptor per beam instead of (descriptor, multiplicity)
     plain = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)

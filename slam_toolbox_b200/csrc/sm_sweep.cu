@@ -545,40 +545,53 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
       //     [0, height) index outside [0, data_size) in the reference and contribute 0;
       //   secondary list (row parity flipped): poses whose column left [0, stride) by less than one stride -- the
       //     reference's linear index (M.cpp:1192-1200) makes them read the neighbouring row at column -/+ stride.
-      //   One thread per (beam, pose), no division. ----
+      //   Every thread owns up to 3 fixed poses (coordinates in registers: no division in the loops) and walks the beams. ----
       {
-        if (f.clip_start[((size_t)q * nA + nA - 1) * 4 + 4] - f.clip_start[(size_t)q * nA * 4] > 0) {
-          const int32_t * cl = f.clip_start + ((size_t)q * nA) * 4 + ph;
-          for (int a = 0; a < nA; ++a) {
-            const int sb = cl[4 * a], se = cl[4 * a + 1];
-            const int work = (se - sb) * P;
-            for (int t = threadIdx.x; t < work; t += blockDim.x) {
-              const int bi = t / P, p = t - bi * P;
-              const int32_t e = f.clip[sb + bi];
-              const int Xb = (int)(int16_t)(e & 0xFFFF), Yb = e >> 16;
-              const int row = Yb + 2 * (p / nX), col = Xb + 2 * (p % nX);
-              if ((unsigned)col >= (unsigned)d.stride || (unsigned)row >= (unsigned)d.height) continue;
-              const int v = S8[(row >> 1) * kPitchB + (col >> 1)];
-              if (v) atomicAdd(A + a * P + p, v);
+        const bool has_edge = f.clip_start[((size_t)q * nA + nA - 1) * 4 + 4] - f.clip_start[(size_t)q * nA * 4] > 0;
+        const bool has_wrap = f.wrap2_start[((size_t)q * nA + nA - 1) * 4 + 4] - f.wrap2_start[(size_t)q * nA * 4] > 0;
+        if (has_edge || has_wrap) {
+          int ex[3], ey[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int p = threadIdx.x + k * kFastThreads;
+            ex[k] = p < P ? 2 * (p % nX) : -100000;   // poses beyond P never hit a valid column
+            ey[k] = 2 * (p / nX);
+          }
+          if (has_edge) {
+            const int32_t * cl = f.clip_start + ((size_t)q * nA) * 4 + ph;
+            for (int a = 0; a < nA; ++a) {
+              int32_t * Aa = A + a * P + threadIdx.x;
+              for (int bi = cl[4 * a]; bi < cl[4 * a + 1]; ++bi) {
+                const int32_t e = f.clip[bi];
+                const int Xb = (int)(int16_t)(e & 0xFFFF), Yb = e >> 16;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                  const int col = Xb + ex[k], row = Yb + ey[k];
+                  if ((unsigned)col >= (unsigned)d.stride || (unsigned)row >= (unsigned)d.height) continue;
+                  const int v = S8[(row >> 1) * kPitchB + (col >> 1)];
+                  if (v) atomicAdd(Aa + k * kFastThreads, v);
+                }
+              }
             }
           }
-        }
-        if (f.wrap2_start[((size_t)q * nA + nA - 1) * 4 + 4] - f.wrap2_start[(size_t)q * nA * 4] > 0) {
-          const int32_t * cl = f.wrap2_start + ((size_t)q * nA) * 4 + ph;
-          for (int a = 0; a < nA; ++a) {
-            const int sb = cl[4 * a], se = cl[4 * a + 1];
-            const int work = (se - sb) * P;
-            for (int t = threadIdx.x; t < work; t += blockDim.x) {
-              const int bi = t / P, p = t - bi * P;
-              const int32_t e = f.wrap2[sb + bi];
-              const int Xb = (int)(int16_t)(e & 0xFFFF), Yb = e >> 16;
-              const int col = Xb + 2 * (p % nX);
-              if ((unsigned)col < (unsigned)d.stride) continue;
-              const int r2 = Yb + 2 * (p / nX) + (col < 0 ? -1 : 1);
-              const int c2 = col + (col < 0 ? d.stride : -d.stride);
-              if ((unsigned)r2 >= (unsigned)d.height) continue;
-              const int v = S8[(r2 >> 1) * kPitchB + (c2 >> 1)];
-              if (v) atomicAdd(A + a * P + p, v);
+          if (has_wrap) {
+            const int32_t * cl = f.wrap2_start + ((size_t)q * nA) * 4 + ph;
+            for (int a = 0; a < nA; ++a) {
+              int32_t * Aa = A + a * P + threadIdx.x;
+              for (int bi = cl[4 * a]; bi < cl[4 * a + 1]; ++bi) {
+                const int32_t e = f.wrap2[bi];
+                const int Xb = (int)(int16_t)(e & 0xFFFF), Yb = e >> 16;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                  const int col = Xb + ex[k];
+                  if ((unsigned)col < (unsigned)d.stride || ex[k] < 0) continue;
+                  const int r2 = Yb + ey[k] + (col < 0 ? -1 : 1);
+                  const int c2 = col + (col < 0 ? d.stride : -d.stride);
+                  if ((unsigned)r2 >= (unsigned)d.height) continue;
+                  const int v = S8[(r2 >> 1) * kPitchB + (c2 >> 1)];
+                  if (v) atomicAdd(Aa + k * kFastThreads, v);
+                }
+              }
             }
           }
         }
@@ -874,7 +887,7 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   S.fast_info[0] = 0; S.fast_info[1] = S.fast_info[2] = S.fast_info[3] = 0;
   auto bail = [&](int why) { S.fast_info[4] = why; return false; };
   if (g.order_dependent) return bail(1);
-  if (nY > 8 * kFastRowTiles || (g.stride & 1)) return bail(2);
+  if (nY > 8 * kFastRowTiles || (g.stride & 1) || nX * nY > 3 * kFastThreads) return bail(2);
   if (g.stride / 2 > kSubPitchW * 4 - 16) return bail(3);   // sub-grid row + the 3-word overhang must fit the pitch
   const int xtiles = (nX + 3 + 15) / 16;
   int sub_rows = (g.height + 1) / 2 + 8;                     // + padding rows read by idle row tiles

@@ -449,6 +449,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
       for (int wi = warp; wi < nA * f.xtiles; wi += nwarps) {
         const int a = wi / f.xtiles, xt = wi - a * f.xtiles;
         const int32_t * cs = f.cls_start + ((size_t)q * nA + a) * 33 + ph * 8;
+        const int32_t * es = f.edge_start + ((size_t)q * nA + a) * 17 + ph * 4;
         const uint32_t base = (uint32_t)((y_l * kSubPitchW + 4 * xt + j_l) * 4);
         int32_t * Arow = A + a * P;
         for (int m = 0; m < 4; ++m) {
@@ -457,6 +458,24 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
           const int mb = cs[2 * m + 1], me = cs[2 * m + 2];
           bool multi_done = (mb == me);
           const int x0 = 4 * (4 * xt + j_l) - m;
+          // flush the 16-bit fields: pose x = x0 + t, t = 0..3 (most windows of a sparse grid are empty)
+          auto flush = [&](const uint32_t (&T0)[kFastRowTiles], const uint32_t (&T1)[kFastRowTiles]) {
+            uint32_t any = 0;
+#pragma unroll
+            for (int r = 0; r < kFastRowTiles; ++r) any |= T0[r] | T1[r];
+            if (!__any_sync(0xffffffffu, any != 0)) return;
+#pragma unroll
+            for (int r = 0; r < kFastRowTiles; ++r) {
+              const int y = y_l + 8 * r;
+              if (y >= nY || (T0[r] | T1[r]) == 0) continue;
+              int32_t * dst = Arow + y * nX + x0;
+              const int v0 = T0[r] & 0xFFFF, v1 = T1[r] & 0xFFFF, v2 = T0[r] >> 16, v3 = T1[r] >> 16;
+              if (v0 && (unsigned)(x0 + 0) < (unsigned)nX) atomicAdd(dst + 0, v0);
+              if (v1 && (unsigned)(x0 + 1) < (unsigned)nX) atomicAdd(dst + 1, v1);
+              if (v2 && (unsigned)(x0 + 2) < (unsigned)nX) atomicAdd(dst + 2, v2);
+              if (v3 && (unsigned)(x0 + 3) < (unsigned)nX) atomicAdd(dst + 3, v3);
+            }
+          };
           do {
             const int ce = min(mb, b + kFastChunk);
             uint32_t T0[kFastRowTiles], T1[kFastRowTiles];
@@ -521,23 +540,38 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
               }
               multi_done = true;
             }
-            // flush the 16-bit fields: pose x = x0 + t, t = 0..3 (most windows of a sparse grid are empty)
-            uint32_t any = 0;
-#pragma unroll
-            for (int r = 0; r < kFastRowTiles; ++r) any |= T0[r] | T1[r];
-            if (!__any_sync(0xffffffffu, any != 0)) continue;
-#pragma unroll
-            for (int r = 0; r < kFastRowTiles; ++r) {
-              const int y = y_l + 8 * r;
-              if (y >= nY || (T0[r] | T1[r]) == 0) continue;
-              int32_t * dst = Arow + y * nX + x0;
-              const int v0 = T0[r] & 0xFFFF, v1 = T1[r] & 0xFFFF, v2 = T0[r] >> 16, v3 = T1[r] >> 16;
-              if (v0 && (unsigned)(x0 + 0) < (unsigned)nX) atomicAdd(dst + 0, v0);
-              if (v1 && (unsigned)(x0 + 1) < (unsigned)nX) atomicAdd(dst + 1, v1);
-              if (v2 && (unsigned)(x0 + 2) < (unsigned)nX) atomicAdd(dst + 2, v2);
-              if (v3 && (unsigned)(x0 + 3) < (unsigned)nX) atomicAdd(dst + 3, v3);
-            }
+            flush(T0, T1);
           } while (b < mb || !multi_done);
+          // EDGE beams of this group (window partly outside the grid): same word loads, but rows / words that fall
+          // outside the sub-grid are skipped (they index outside [0, data_size) or wrap in the reference; the wrapped
+          // part is added by the secondary list below). Rows / words inside the allocation but beyond the valid cells
+          // are zero padding, so only the allocation bounds need checking.
+          int eb = es[m];
+          const int ee = es[m + 1];
+          while (eb < ee) {
+            const int ce = min(ee, eb + kFastChunk);
+            uint32_t T0[kFastRowTiles], T1[kFastRowTiles];
+#pragma unroll
+            for (int r = 0; r < kFastRowTiles; ++r) { T0[r] = 0; T1[r] = 0; }
+            for (int b0 = eb; b0 < ce; b0 += 32) {
+              const int cnt = min(32, ce - b0);
+              const int32_t mine = (lane < cnt) ? f.edge[b0 + lane] : 0;
+              for (int k = 0; k < cnt; ++k) {
+                const int32_t e = __shfl_sync(0xffffffffu, mine, k);
+                const int row0 = (int)(int16_t)(e & 0xFFFF) + y_l, wq = (e >> 16) + 4 * xt + j_l;
+                const bool cv = (unsigned)wq < (unsigned)kSubPitchW;
+#pragma unroll
+                for (int r = 0; r < kFastRowTiles; ++r) {
+                  const int row = row0 + 8 * r;
+                  const uint32_t w = (cv && (unsigned)row < (unsigned)f.sub_rows) ? S[row * kSubPitchW + wq] : 0u;
+                  T0[r] += even_bytes(w);
+                  T1[r] += odd_bytes(w);
+                }
+              }
+            }
+            eb = ce;
+            flush(T0, T1);
+          }
         }
       }
       // ---- EDGE beams: the window leaves the grid (readings close to / beyond the range threshold).
@@ -547,32 +581,14 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
       //     reference's linear index (M.cpp:1192-1200) makes them read the neighbouring row at column -/+ stride.
       //   Every thread owns up to 3 fixed poses (coordinates in registers: no division in the loops) and walks the beams. ----
       {
-        const bool has_edge = f.clip_start[((size_t)q * nA + nA - 1) * 4 + 4] - f.clip_start[(size_t)q * nA * 4] > 0;
         const bool has_wrap = f.wrap2_start[((size_t)q * nA + nA - 1) * 4 + 4] - f.wrap2_start[(size_t)q * nA * 4] > 0;
-        if (has_edge || has_wrap) {
+        if (has_wrap) {
           int ex[3], ey[3];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const int p = threadIdx.x + k * kFastThreads;
             ex[k] = p < P ? 2 * (p % nX) : -100000;   // poses beyond P never hit a valid column
             ey[k] = 2 * (p / nX);
-          }
-          if (has_edge) {
-            const int32_t * cl = f.clip_start + ((size_t)q * nA) * 4 + ph;
-            for (int a = 0; a < nA; ++a) {
-              int32_t * Aa = A + a * P + threadIdx.x;
-              for (int bi = cl[4 * a]; bi < cl[4 * a + 1]; ++bi) {
-                const int32_t e = f.clip[bi];
-                const int Xb = (int)(int16_t)(e & 0xFFFF), Yb = e >> 16;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                  const int col = Xb + ex[k], row = Yb + ey[k];
-                  if ((unsigned)col >= (unsigned)d.stride || (unsigned)row >= (unsigned)d.height) continue;
-                  const int v = S8[(row >> 1) * kPitchB + (col >> 1)];
-                  if (v) atomicAdd(Aa + k * kFastThreads, v);
-                }
-              }
-            }
           }
           if (has_wrap) {
             const int32_t * cl = f.wrap2_start + ((size_t)q * nA) * 4 + ph;
@@ -899,6 +915,8 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   std::vector<int32_t> origin(2 * (size_t)nq), cls_start((size_t)nq * nA * 33), slow, slow_start((size_t)nq * (nA + 1));
   std::vector<uint16_t> beams, mult;
   std::vector<int32_t> clip, clip_start((size_t)nq * nA * 4 + 1), wrap2, wrap2_start((size_t)nq * nA * 4 + 1);
+  std::vector<int32_t> edge, edge_start((size_t)nq * nA * 17);
+  int n_edge = 0;
   beams.reserve((size_t)nq * nA * n);
   mult.reserve((size_t)nq * nA * n);
   for (int q = 0; q < nq; ++q) {
@@ -908,11 +926,12 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
     const int X0 = pl.xs[0], Y0 = pl.ys[0];
     origin[2 * q] = X0; origin[2 * q + 1] = Y0;
     std::vector<uint16_t> group[16];
-    std::vector<int32_t> cgroup[4], wgroup[4];
+    std::vector<int32_t> cgroup[4], wgroup[4], egroup[16];
     for (int a = 0; a < nA; ++a) {
       for (auto & v : group) v.clear();
       for (auto & v : cgroup) v.clear();
       for (auto & v : wgroup) v.clear();
+      for (auto & v : egroup) v.clear();
       slow_start[(size_t)q * (nA + 1) + a] = (int32_t)slow.size();
       for (int i = 0; i < n; ++i) {
         const int32_t off = pl.offsets[(size_t)a * n + i];
@@ -930,7 +949,11 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
           const int32_t e = (int32_t)((uint32_t)(Xb & 0xFFFF) | ((uint32_t)Yb << 16));
           const bool rows_hit = Yb + 2 * (nY - 1) >= 0 && Yb < g.height;
           const bool cols_hit = Xb + 2 * (nX - 1) >= 0 && Xb < g.stride;
-          if (rows_hit && cols_hit) cgroup[(Yb & 1) * 2 + (Xb & 1)].push_back(e);
+          if (rows_hit && cols_hit) {
+            const int c = Xb >> 1, r = Yb >> 1;   // arithmetic shifts: floor for negative coordinates
+            egroup[((Yb & 1) * 2 + (Xb & 1)) * 4 + (c & 3)].push_back((int32_t)((uint32_t)(r & 0xFFFF) | ((uint32_t)(c >> 2) << 16)));
+            ++n_edge;
+          }
           const bool wraps = Xb < 0 || Xb + 2 * (nX - 1) >= g.stride;
           if (wraps && Yb + 2 * (nY - 1) + 1 >= 0 && Yb - 1 < g.height) wgroup[((Yb & 1) ^ 1) * 2 + (Xb & 1)].push_back(e);
         } else {
@@ -944,6 +967,11 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
         wrap2_start[((size_t)q * nA + a) * 4 + k] = (int32_t)wrap2.size();
         wrap2.insert(wrap2.end(), wgroup[k].begin(), wgroup[k].end());
       }
+      for (int k = 0; k < 16; ++k) {
+        edge_start[((size_t)q * nA + a) * 17 + k] = (int32_t)edge.size();
+        edge.insert(edge.end(), egroup[k].begin(), egroup[k].end());
+      }
+      edge_start[((size_t)q * nA + a) * 17 + 16] = (int32_t)edge.size();
       int32_t * cs = &cls_start[((size_t)q * nA + a) * 33];
       for (int k = 0; k < 16; ++k) {
         std::vector<uint16_t> & gk = group[k];
@@ -986,13 +1014,16 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   wrap2.push_back(0);
   h2d(S.d_fast_clip, clip.data(), clip.size(), st);
   h2d(S.d_fast_clip_start, clip_start.data(), clip_start.size(), st);
+  edge.push_back(0);
+  h2d(S.d_fast_edge, edge.data(), edge.size(), st);
+  h2d(S.d_fast_edge_start, edge_start.data(), edge_start.size(), st);
   h2d(S.d_fast_wrap2, wrap2.data(), wrap2.size(), st);
   h2d(S.d_fast_wrap2_start, wrap2_start.data(), wrap2_start.size(), st);
   h2d(S.d_fast_slow, slow.data(), slow.size(), st);
   h2d(S.d_fast_slow_start, slow_start.data(), slow_start.size(), st);
   B200_CUDA(cudaStreamSynchronize(st));   // the vectors above go out of scope
   S.fast.enabled = 1;
-  S.fast_info[0] = 1; S.fast_info[1] = (int32_t)beams.size(); S.fast_info[2] = (int32_t)clip.size() - 1; S.fast_info[3] = (int32_t)slow.size() - 1; S.fast_info[4] = 0;
+  S.fast_info[0] = 1; S.fast_info[1] = (int32_t)beams.size(); S.fast_info[2] = n_edge; S.fast_info[3] = (int32_t)slow.size() - 1; S.fast_info[4] = 0;
   S.fast.sub_rows = sub_rows;
   S.fast.xtiles = xtiles;
   S.fast.origin = S.d_fast_origin.p;
@@ -1002,6 +1033,8 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   S.fast.slow = S.d_fast_slow.p;
   S.fast.clip = S.d_fast_clip.p;
   S.fast.clip_start = S.d_fast_clip_start.p;
+  S.fast.edge = S.d_fast_edge.p;
+  S.fast.edge_start = S.d_fast_edge_start.p;
   S.fast.wrap2 = S.d_fast_wrap2.p;
   S.fast.wrap2_start = S.d_fast_wrap2_start.p;
   S.fast.slow_start = S.d_fast_slow_start.p;

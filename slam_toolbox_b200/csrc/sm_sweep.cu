@@ -914,7 +914,7 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   if ((size_t)5 * nX * nY * sizeof(double) > (size_t)sub_rows * kSubPitchW * 4) return bail(5);   // epilogue scratch reuses S
   std::vector<int32_t> origin(2 * (size_t)nq), cls_start((size_t)nq * nA * 33), slow, slow_start((size_t)nq * (nA + 1));
   std::vector<uint16_t> beams, mult;
-  std::vector<int32_t> clip, clip_start((size_t)nq * nA * 4 + 1), wrap2, wrap2_start((size_t)nq * nA * 4 + 1);
+  std::vector<int32_t> wrap2, wrap2_start((size_t)nq * nA * 4 + 1);
   std::vector<int32_t> edge, edge_start((size_t)nq * nA * 17);
   int n_edge = 0;
   beams.reserve((size_t)nq * nA * n);
@@ -926,10 +926,9 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
     const int X0 = pl.xs[0], Y0 = pl.ys[0];
     origin[2 * q] = X0; origin[2 * q + 1] = Y0;
     std::vector<uint16_t> group[16];
-    std::vector<int32_t> cgroup[4], wgroup[4], egroup[16];
+    std::vector<int32_t> wgroup[4], egroup[16];
     for (int a = 0; a < nA; ++a) {
       for (auto & v : group) v.clear();
-      for (auto & v : cgroup) v.clear();
       for (auto & v : wgroup) v.clear();
       for (auto & v : egroup) v.clear();
       slow_start[(size_t)q * (nA + 1) + a] = (int32_t)slow.size();
@@ -962,8 +961,6 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
         }
       }
       for (int k = 0; k < 4; ++k) {
-        clip_start[((size_t)q * nA + a) * 4 + k] = (int32_t)clip.size();
-        clip.insert(clip.end(), cgroup[k].begin(), cgroup[k].end());
         wrap2_start[((size_t)q * nA + a) * 4 + k] = (int32_t)wrap2.size();
         wrap2.insert(wrap2.end(), wgroup[k].begin(), wgroup[k].end());
       }
@@ -999,7 +996,6 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
     }
     slow_start[(size_t)q * (nA + 1) + nA] = (int32_t)slow.size();
   }
-  clip_start[(size_t)nq * nA * 4] = (int32_t)clip.size();
   wrap2_start[(size_t)nq * nA * 4] = (int32_t)wrap2.size();
   // slow_start must be relative to one array: it is (single vector `slow`)
   h2d(S.d_fast_origin, origin.data(), origin.size(), st);
@@ -1010,10 +1006,7 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   if (!mult.empty()) B200_CUDA(cudaMemcpyAsync(S.d_fast_mult.p, mult.data(), mult.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
   S.h2d_bytes += (int64_t)(2 * beams.size() * sizeof(uint16_t));
   slow.push_back(0);
-  clip.push_back(0);
   wrap2.push_back(0);
-  h2d(S.d_fast_clip, clip.data(), clip.size(), st);
-  h2d(S.d_fast_clip_start, clip_start.data(), clip_start.size(), st);
   edge.push_back(0);
   h2d(S.d_fast_edge, edge.data(), edge.size(), st);
   h2d(S.d_fast_edge_start, edge_start.data(), edge_start.size(), st);
@@ -1031,8 +1024,6 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   S.fast.mult = S.d_fast_mult.p;
   S.fast.cls_start = S.d_fast_cls.p;
   S.fast.slow = S.d_fast_slow.p;
-  S.fast.clip = S.d_fast_clip.p;
-  S.fast.clip_start = S.d_fast_clip_start.p;
   S.fast.edge = S.d_fast_edge.p;
   S.fast.edge_start = S.d_fast_edge_start.p;
   S.fast.wrap2 = S.d_fast_wrap2.p;

@@ -132,8 +132,6 @@ struct FastDev {
   const uint16_t * beams;        // FAST descriptors, grouped; per group: plain entries, then multi entries
   const uint16_t * mult;         // multiplicity of every entry (1 for plain entries)
   const int32_t * cls_start;     // [nq][nA][33]: group g = phase * 4 + m -> [2g] plain begin, [2g+1] multi begin, [2g+2] end
-  const int32_t * clip;          // EDGE beams, primary entries (own phase): Xb | Yb << 16 per beam
-  const int32_t * clip_start;    // [nq][nA][4] + 1, per phase
   const int32_t * edge;          // EDGE beams in word form, grouped like the FAST lists: sub-row | word << 16 (both signed 16 bit)
   const int32_t * edge_start;    // [nq][nA][17]
   const int32_t * wrap2;         // EDGE beams whose columns leave [0, stride): secondary entries (row parity flipped)
@@ -164,7 +162,7 @@ struct SweepHost {
   DevBuf<double> d_qgeom, d_center, d_qd, d_angpen, d_points, d_ws_probs;
   DevBuf<uint8_t> d_ws_grid, d_kernel;
   DevBuf<uint16_t> d_fast_beams, d_fast_mult;
-  DevBuf<int32_t> d_fast_origin, d_fast_cls, d_fast_slow, d_fast_slow_start, d_fast_clip, d_fast_clip_start, d_fast_wrap2, d_fast_wrap2_start, d_fast_edge, d_fast_edge_start;
+  DevBuf<int32_t> d_fast_origin, d_fast_cls, d_fast_slow, d_fast_slow_start, d_fast_wrap2, d_fast_wrap2_start, d_fast_edge, d_fast_edge_start;
   FastDev fast{};
   size_t fast_smem = 0;
   int32_t fast_info[5] = {0, 0, 0, 0, 0};   // enabled, FAST descriptors, CLIP beams, WRAP beams, reason the fast path was refused

@@ -1,6 +1,7 @@
 """Ad-hoc GPU bring-up check (not a pytest file): CUDA path vs C-port oracle on a few cases."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from slam_toolbox_b200 import synth
 import helpers as H

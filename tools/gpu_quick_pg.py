@@ -1,6 +1,7 @@
 """Ad-hoc GPU bring-up check of the pose-graph solver against the restated-Ceres oracle."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from slam_toolbox_b200 import synth, api
 from oracle import posegraph as PG

@@ -4,7 +4,7 @@
 Metric (BASELINE.json): scan matches/sec (1081-beam, +-2 m / +-20 deg) on the loop-closure
 batch workload (configs[1]: 1 query x 1000 candidate 1081-beam scans per GPU), plus the
 10k-node / 40k-edge SE(2) pose-graph solve time (configs[3]) reported in the same JSON line
-under "graph_solve".
+under "graph_solve", and the map-publish step (occupancy grid from 5,000 scans) under "occupancy_grid".
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
@@ -249,6 +249,54 @@ def graph_solve_bench(steps: int, with_cpu: bool):
     return out
 
 
+def occupancy_bench(steps: int, with_cpu: bool):
+    """Map publish (SURVEY.md 8f row 4): OccupancyGrid::CreateFromScans over a cfg3-sized run of 5,000 scans at 0.05 m."""
+    from slam_toolbox_b200 import synth, api
+    n_scans, res = 5000, 0.05
+    run = synth.make_mapping_run(3, n_scans, world=synth.make_world(3, size=60.0), odd_readings=False)
+    blk = api.ScanBlock(run["ranges"], run["poses"], api.LaserRangeFinder())
+    g = api.OccupancyGrid(res, blk.laser)
+    g.AddScans(blk)
+    g.Build()                                    # warm-up: allocations
+    ms = []
+    for _ in range(steps):
+        g.Build()
+        ms.append(g.kernel_ms())
+    cells, ps, ht = g.GetData(counters=True)
+    updates = int(ps.sum())
+    launches = g.launch_count()
+    g.close()
+    e2e = []
+    for _ in range(2):                           # through the public one-shot call: H2D of all scans + build + cells D2H
+        t = time.perf_counter()
+        g2 = api.OccupancyGrid.CreateFromScans(blk, res)
+        c2 = g2.GetData()
+        e2e.append((time.perf_counter() - t) * 1e3)
+        g2.close()
+    out = {"scans": n_scans, "beams": int(run["ranges"].size), "resolution": res, "grid": [int(cells.shape[1]), int(cells.shape[0])],
+           "ms": float(np.mean(ms)), "scans_per_s": n_scans / (float(np.mean(ms)) * 1e-3), "cell_updates": updates,
+           "cell_updates_per_s": updates / (float(np.mean(ms)) * 1e-3), "e2e_ms": float(min(e2e)),
+           "h2d_bytes": int(run["ranges"].nbytes * 3 + run["poses"].shape[0] * 20), "d2h_bytes": int(cells.nbytes),
+           "kernel_launches_per_build": 3, "kernel_launches": int(launches)}
+    if with_cpu:
+        from oracle import karto_ref as R, karto_port as P
+        if R.available():
+            R.init_laser(min_angle=synth.ANGLE_MIN, max_angle=synth.ANGLE_MAX, ang_res=synth.ANGLE_INC, min_range=0.1, max_range=30.0,
+                         range_threshold=12.0)
+            scans = [R.RefScan(r, p, i) for i, (r, p) in enumerate(zip(run["ranges"], run["poses"]))]
+            ref = R.occupancy(scans, res)
+            kind = "reference"
+        else:
+            scans = [P.PortScan(r, p, synth.ANGLE_MIN, synth.ANGLE_INC) for r, p in zip(run["ranges"], run["poses"])]
+            ref = P.occupancy(scans, res, 12.0, 0.1, 30.0)
+            kind = "port"
+        out["cpu_baseline"] = {"ms": ref["seconds"] * 1e3, "kind": kind, "cores": 1,
+                               "what": "OccupancyGrid::CreateFromScans on the same scans (single-threaded in the reference)"}
+        out["parity_exact"] = bool(np.array_equal(ref["cells"], cells) and np.array_equal(ref["passes"], ps) and np.array_equal(ref["hits"], ht)
+                                   and np.array_equal(c2, cells))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -256,6 +304,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="skip the pose-graph solve part")
+    ap.add_argument("--no-map", action="store_true", help="skip the occupancy-grid (map publish) part")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--chain-len", type=int, default=CHAIN_LEN)
     ap.add_argument("--candidates", type=int, default=N_CAND)
@@ -429,6 +478,8 @@ def main():
     }
     if not args.no_graph:
         line["graph_solve"] = graph_solve_bench(3, not args.no_cpu)
+    if not args.no_map:
+        line["occupancy_grid"] = occupancy_bench(5, not args.no_cpu)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

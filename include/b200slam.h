@@ -227,6 +227,67 @@ int b200pg_solve(b200pg * h, b200pg_summary * summary_or_null);
  * written (<= cap). Empty after b200pg_clear(). */
 int32_t b200pg_get_corrections(const b200pg * h, int32_t * ids, double * poses, int32_t cap);
 
+/* ------------------------------------------------------------------------------------------
+ * Occupancy grid: karto::OccupancyGrid::CreateFromScans (Karto.h:5946-5961), the map-publish step
+ * next to the hot path (slam_toolbox: SMapper::getOccupancyGrid src/slam_mapper.cpp:63-69, called
+ * from SlamToolbox::updateMap src/slam_toolbox_common.cpp:630-654 with ALL processed scans).
+ *
+ * The scans live in HBM behind the handle: append them as the mapper processes them (or re-load
+ * them after a loop closure moved their poses), then build as often as a map is wanted.  A build
+ * is: bounding box of the scans (ComputeDimensions Karto.h:6082-6107) -> one Bresenham trace per
+ * beam into the pass / hit counters (AddScan Karto.h:6139-6182, RayTrace :6193-6229, TraceLine
+ * :4874-4927) -> cell states (Update :6259-6274).  Counters are integers, so the result is
+ * bit-identical to the reference's whatever the order the beams are traced in.
+ * ---------------------------------------------------------------------------------------- */
+#define B200_CELL_UNKNOWN 0      /* GridStates_Unknown  Karto.h:4379 */
+#define B200_CELL_OCCUPIED 100   /* GridStates_Occupied Karto.h:4380 */
+#define B200_CELL_FREE 255       /* GridStates_Free     Karto.h:4381 */
+
+typedef struct b200og_params {
+  double resolution;           /* m per cell (CreateFromScans' argument); 0 is rejected (Karto.h:5916-5918) */
+  double range_threshold;      /* LaserRangeFinder::GetRangeThreshold(): longer readings are traced up to it, without a hit */
+  double minimum_range;        /* LaserRangeFinder::GetMinimumRange(): readings <= it are ignored (Karto.h:6160) */
+  double maximum_range;        /* LaserRangeFinder::GetMaximumRange(): readings >= it are ignored              */
+  uint32_t min_pass_through;   /* OccupancyGrid "MinPassThrough", 2   (Karto.h:5921, :6241) */
+  double occupancy_threshold;  /* OccupancyGrid "OccupancyThreshold", 0.1 (Karto.h:5922, :6246) */
+} b200og_params;
+
+typedef struct b200og_info {
+  int32_t width, height;       /* Round(bounding-box size / resolution) (Karto.h:6103-6105) */
+  int32_t stride;              /* width step: width aligned up to 8 (Karto.h:4640); rows of every array below */
+  double offset[2];            /* world position of cell (0,0) = bounding-box minimum (Karto.h:6106) */
+} b200og_info;
+
+typedef struct b200og b200og;
+
+/* Karto's defaults for everything but the laser limits (12 m / 0.1 m / 30 m here) */
+void b200og_default_params(b200og_params * p);
+int b200og_create(const b200og_params * params, b200og ** out);
+void b200og_destroy(b200og * h);
+int b200og_set_stream(b200og * h, void * cuda_stream);
+/* The scan store.  add = copy n scans (ranges, unfiltered point readings, sensor position) to the
+ * device, after the scans already there; clear = forget them all. */
+int b200og_add_scans(b200og * h, const b200_scan * scans, int32_t n);
+int b200og_clear_scans(b200og * h);
+int32_t b200og_num_scans(const b200og * h);
+/* CreateFromScans over the stored scans.  With no scans the reference returns NULL: here
+ * B200_ERR_NOT_FOUND, *info zeroed.  B200_ERR_UNSUPPORTED when width step * height exceeds 2^31-1
+ * (the reference's kt_int32s data size overflows there too). */
+int b200og_build(b200og * h, b200og_info * info);
+/* Result of the last build, each array stride * height, any pointer may be NULL:
+ * cells = the grid's bytes (B200_CELL_*), pass / hits = the counters behind them. */
+int b200og_fetch(b200og * h, uint8_t * cells, uint32_t * pass, uint32_t * hits);
+/* the same bytes as a nav_msgs/OccupancyGrid payload (width * height, row-major, -1 / 100 / 0:
+ * vis_utils::toNavMap include/slam_toolbox/visualization_utils.hpp:108-146) */
+int b200og_fetch_nav(b200og * h, int8_t * data);
+/* device time of the last build's kernels (ms) and the kernels it launched */
+int b200og_kernel_ms(b200og * h, float * ms);
+int64_t b200og_launch_count(const b200og * h);
+/* The static entry point in one call: create + add_scans + build.  *out stays NULL (and the call
+ * returns B200_ERR_NOT_FOUND) for n == 0, like the reference's NULL. */
+int b200og_create_from_scans(const b200og_params * params, const b200_scan * scans, int32_t n, b200og_info * info,
+                             b200og ** out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -550,3 +550,108 @@ const uint8_t * kp_grid(kp_matcher * m, int32_t info[9], double off[2])
   return g->data;
 }
 const uint8_t * kp_kernel(kp_matcher * m) { return m->g.kernel; }
+
+/* ======== occupancy grid: karto::OccupancyGrid::CreateFromScans (K.h:5946-5961) ============ */
+struct kp_occupancy {
+  int32_t width, height, stride;   /* K.h:4636-4640 */
+  double scale, off_x, off_y;
+  uint8_t * cells;                 /* Grid<kt_int8u>  */
+  uint32_t * pass, * hits;         /* K.h:6292-6297   */
+};
+
+/* Grid<T>::TraceLine K.h:4874-4927: every visited valid cell gets ++ */
+static void kp_trace_line(kp_occupancy * g, int32_t x0, int32_t y0, int32_t x1, int32_t y1)
+{
+  int steep = abs(y1 - y0) > abs(x1 - x0);
+  int32_t t, deltaX, deltaY, error = 0, ystep, y, x;
+  if (steep) { t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; }
+  if (x0 > x1) { t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
+  deltaX = x1 - x0;
+  deltaY = abs(y1 - y0);
+  y = y0;
+  ystep = y0 < y1 ? 1 : -1;
+  for (x = x0; x <= x1; x++) {
+    int32_t px = steep ? y : x, py = steep ? x : y;
+    error += deltaY;
+    if (2 * error >= deltaX) { y += ystep; error -= deltaX; }
+    if (kp_is_up_to(px, g->width) && kp_is_up_to(py, g->height)) g->pass[px + py * g->stride]++;
+  }
+}
+
+kp_occupancy * kp_occupancy_create(const kp_scan * scans, int32_t n, double resolution, double range_threshold,
+                                   double minimum_range, double maximum_range, uint32_t min_pass_through,
+                                   double occupancy_threshold)
+{
+  double minx = 999999999999999999.99999, miny = minx, maxx = -minx, maxy = -minx;   /* K.h:2845-2849 */
+  kp_occupancy * g;
+  int32_t s, i;
+  size_t cells, c;
+  if (n <= 0) return NULL;                                                            /* K.h:5950-5952 */
+  /* ComputeDimensions K.h:6082-6107 over the scans' bounding boxes (LocalizedRangeScan::Update K.h:5692-5698) */
+  for (s = 0; s < n; ++s) {
+    const kp_scan * sc = &scans[s];
+#define KP_BOX(x, y) do { if ((x) < minx) minx = (x); if ((y) < miny) miny = (y); if ((x) > maxx) maxx = (x); if ((y) > maxy) maxy = (y); } while (0)
+    KP_BOX(sc->sensor_pose[0], sc->sensor_pose[1]);
+    for (i = 0; i < sc->n; ++i) {
+      double r = sc->ranges[i];
+      if (r >= minimum_range && r <= range_threshold) KP_BOX(sc->points_xy[2 * i], sc->points_xy[2 * i + 1]);   /* InRange Math.h:123 */
+    }
+#undef KP_BOX
+  }
+  g = (kp_occupancy *)calloc(1, sizeof(*g));
+  g->scale = 1.0 / resolution;
+  g->width = kp_to_int(kp_round((maxx - minx) * g->scale));
+  g->height = kp_to_int(kp_round((maxy - miny) * g->scale));
+  g->stride = (g->width + 7) & ~7;                                                    /* AlignValue K.h:4640 */
+  g->off_x = minx; g->off_y = miny;
+  cells = (size_t)g->stride * (size_t)g->height;
+  g->cells = (uint8_t *)calloc(cells ? cells : 1, 1);
+  g->pass = (uint32_t *)calloc(cells ? cells : 1, sizeof(uint32_t));
+  g->hits = (uint32_t *)calloc(cells ? cells : 1, sizeof(uint32_t));
+  /* AddScan K.h:6139-6182 + RayTrace K.h:6193-6229 */
+  for (s = 0; s < n; ++s) {
+    const kp_scan * sc = &scans[s];
+    double sx = sc->sensor_pose[0], sy = sc->sensor_pose[1];
+    for (i = 0; i < sc->n; ++i) {
+      double r = sc->ranges[i], px = sc->points_xy[2 * i], py = sc->points_xy[2 * i + 1];
+      int valid_end = r < (range_threshold - KP_TOLERANCE);
+      int32_t fx, fy, tx, ty;
+      if (r <= minimum_range || r >= maximum_range || isnan(r)) continue;
+      if (r >= range_threshold) {
+        double ratio = range_threshold / r, dx = px - sx, dy = py - sy;
+        px = sx + ratio * dx;
+        py = sy + ratio * dy;
+      }
+      kp_world_to_grid(g->scale, g->off_x, g->off_y, sx, sy, &fx, &fy);
+      kp_world_to_grid(g->scale, g->off_x, g->off_y, px, py, &tx, &ty);
+      kp_trace_line(g, fx, fy, tx, ty);
+      if (valid_end && kp_is_up_to(tx, g->width) && kp_is_up_to(ty, g->height)) {
+        g->pass[tx + ty * g->stride]++;
+        g->hits[tx + ty * g->stride]++;
+      }
+    }
+  }
+  /* Update K.h:6259-6274 / UpdateCell K.h:6241-6254 */
+  for (c = 0; c < cells; ++c) {
+    if (g->pass[c] > min_pass_through) {
+      double ratio = (double)g->hits[c] / (double)g->pass[c];
+      g->cells[c] = ratio > occupancy_threshold ? 100 : 255;   /* GridStates K.h:4379-4381 */
+    }
+  }
+  return g;
+}
+
+void kp_occupancy_destroy(kp_occupancy * g)
+{
+  if (!g) return;
+  free(g->cells); free(g->pass); free(g->hits); free(g);
+}
+
+void kp_occupancy_info(const kp_occupancy * g, int32_t info[3], double offset[2])
+{
+  info[0] = g->width; info[1] = g->height; info[2] = g->stride;
+  offset[0] = g->off_x; offset[1] = g->off_y;
+}
+const uint8_t * kp_occupancy_cells(const kp_occupancy * g) { return g->cells; }
+const uint32_t * kp_occupancy_pass(const kp_occupancy * g) { return g->pass; }
+const uint32_t * kp_occupancy_hits(const kp_occupancy * g) { return g->hits; }

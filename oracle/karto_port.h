@@ -74,6 +74,20 @@ int32_t kp_offsets(kp_matcher * m, const kp_scan * query, double angle_center, d
 const uint8_t * kp_grid(kp_matcher * m, int32_t info[9], double off[2]);
 const uint8_t * kp_kernel(kp_matcher * m);
 
+/* karto::OccupancyGrid::CreateFromScans (Karto.h:5946-5961): hit / pass counters by Bresenham traces
+ * (Karto.h:4874-4927, 6139-6229), then cell states 0 unknown / 100 occupied / 255 free (Karto.h:6241-6274).
+ * NULL for n <= 0.  Laser limits are those of the scans' LaserRangeFinder. */
+typedef struct kp_occupancy kp_occupancy;
+kp_occupancy * kp_occupancy_create(const kp_scan * scans, int32_t n, double resolution, double range_threshold,
+                                   double minimum_range, double maximum_range, uint32_t min_pass_through,
+                                   double occupancy_threshold);
+void kp_occupancy_destroy(kp_occupancy * g);
+/* info = {width, height, width step}; offset = world position of cell (0,0) */
+void kp_occupancy_info(const kp_occupancy * g, int32_t info[3], double offset[2]);
+const uint8_t * kp_occupancy_cells(const kp_occupancy * g);
+const uint32_t * kp_occupancy_pass(const kp_occupancy * g);
+const uint32_t * kp_occupancy_hits(const kp_occupancy * g);
+
 #ifdef __cplusplus
 }
 #endif

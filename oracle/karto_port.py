@@ -52,6 +52,14 @@ def lib():
         L.kp_kernel.argtypes = [C.c_void_p]
         L.kp_point_readings.argtypes = [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double), C.c_double, C.c_double,
                                         C.POINTER(C.c_double)]
+        L.kp_occupancy_create.restype = C.c_void_p
+        L.kp_occupancy_create.argtypes = [C.POINTER(KpScan), C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                          C.c_uint32, C.c_double]
+        L.kp_occupancy_destroy.argtypes = [C.c_void_p]
+        L.kp_occupancy_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        for f, t in (("cells", C.c_uint8), ("pass", C.c_uint32), ("hits", C.c_uint32)):
+            getattr(L, "kp_occupancy_" + f).restype = C.POINTER(t)
+            getattr(L, "kp_occupancy_" + f).argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -154,3 +162,28 @@ def find_valid_points(scan, viewpoint):
     out = np.empty((scan.c.n, 2), dtype=np.float64)
     n = lib().kp_find_valid_points(C.byref(scan.c), _dp(vp), _dp(out))
     return out[:n].copy()
+
+
+def occupancy(scans, resolution, range_threshold, minimum_range, maximum_range, min_pass_through=2,
+              occupancy_threshold=0.1):
+    """kp_occupancy_create on PortScan objects; same dict as oracle.karto_ref.occupancy (None when empty)."""
+    import time
+    arr = scan_array(scans)
+    t = time.perf_counter()
+    h = lib().kp_occupancy_create(arr, len(scans), resolution, range_threshold, minimum_range, maximum_range,
+                                  min_pass_through, occupancy_threshold)
+    dt = time.perf_counter() - t
+    if not h:
+        return None
+    info = (C.c_int32 * 3)()
+    off = np.zeros(2)
+    lib().kp_occupancy_info(h, info, _dp(off))
+    w, hh, st = info[0], info[1], info[2]
+    n = hh * st
+    def grab(fn, dt_):
+        p = fn(h)
+        return np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].reshape(hh, st).astype(dt_, copy=True)
+    out = dict(width=w, height=hh, stride=st, offset=off, cells=grab(lib().kp_occupancy_cells, np.uint8),
+               passes=grab(lib().kp_occupancy_pass, np.uint32), hits=grab(lib().kp_occupancy_hits, np.uint32), seconds=dt)
+    lib().kp_occupancy_destroy(h)
+    return out

@@ -55,6 +55,11 @@ def lib():
                                  C.c_int, C.c_int, C.c_int, _DP, _DP, _DP]
         L.kref_link_info.argtypes = [_DP] * 5
         L.kref_matrix3_inverse.argtypes = [_DP, _DP]
+        L.kref_occupancy_create.restype = C.c_void_p
+        L.kref_occupancy_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_double, C.c_int, C.c_double]
+        L.kref_occupancy_destroy.argtypes = [C.c_void_p]
+        L.kref_occupancy_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), _DP]
+        L.kref_occupancy_copy.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
 
@@ -193,3 +198,27 @@ def matrix3_inverse(m):
     out = np.zeros(9)
     lib().kref_matrix3_inverse(_dp(m), _dp(out))
     return out.reshape(3, 3)
+
+
+def occupancy(scans, resolution, min_pass_through=-1, occupancy_threshold=-1.0, counters=True):
+    """karto::OccupancyGrid::CreateFromScans (Karto.h:5946-5961) on RefScan objects.  Negative parameters =
+    the reference's static entry point with its defaults (2, 0.1).  Returns None for an empty scan list, else
+    dict(width, height, stride, offset, cells[h, stride] u8, pass / hits [h, stride] u32, seconds)."""
+    import time
+    t = time.perf_counter()
+    h = lib().kref_occupancy_create(_ptrs(scans), len(scans), float(resolution), int(min_pass_through), float(occupancy_threshold))
+    dt = time.perf_counter() - t
+    if not h:
+        return None
+    info = (C.c_int * 3)()
+    off = np.zeros(2)
+    lib().kref_occupancy_info(h, info, _dp(off))
+    w, hh, st = info[0], info[1], info[2]
+    cells = np.zeros((hh, st), dtype=np.uint8)
+    ps = np.zeros((hh, st), dtype=np.uint32) if counters else None
+    ht = np.zeros((hh, st), dtype=np.uint32) if counters else None
+    lib().kref_occupancy_copy(h, cells.ctypes.data_as(C.POINTER(C.c_uint8)),
+                              ps.ctypes.data_as(C.POINTER(C.c_uint32)) if counters else None,
+                              ht.ctypes.data_as(C.POINTER(C.c_uint32)) if counters else None)
+    lib().kref_occupancy_destroy(h)
+    return dict(width=w, height=hh, stride=st, offset=off, cells=cells, passes=ps, hits=ht, seconds=dt)

@@ -306,4 +306,42 @@ void kref_matrix3_inverse(const double m[9], double out[9])
   for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) out[3 * r + k] = inv(r, k);
 }
 
+// ---- occupancy grid (Karto.h:5883-6330) ----------------------------------------------------
+// karto::OccupancyGrid::CreateFromScans (Karto.h:5946-5961) as slam_toolbox calls it
+// (src/slam_mapper.cpp:63-69).  min_pass_through < 0 and occupancy_threshold < 0 take the static
+// entry point untouched (defaults 2 and 0.1, Karto.h:5921-5922); otherwise the same three steps are
+// issued here with the two parameters set before the counters are evaluated.
+void * kref_occupancy_create(void ** scans, int n, double resolution, int min_pass_through, double occupancy_threshold)
+{
+  LocalizedRangeScanVector v;
+  for (int i = 0; i < n; ++i) v.push_back(static_cast<LocalizedRangeScan *>(scans[i]));
+  if (min_pass_through < 0 && occupancy_threshold < 0) return OccupancyGrid::CreateFromScans(v, resolution);
+  if (v.empty()) return nullptr;
+  kt_int32s w, h; Vector2<kt_double> off;
+  OccupancyGrid::ComputeDimensions(v, resolution, w, h, off);
+  OccupancyGrid * g = new OccupancyGrid(w, h, off, resolution);
+  if (min_pass_through >= 0) g->SetMinPassThrough(static_cast<kt_int32u>(min_pass_through));
+  if (occupancy_threshold >= 0) g->SetOccupancyThreshold(occupancy_threshold);
+  g->CreateFromScans(v);
+  return g;
+}
+void kref_occupancy_destroy(void * g) { delete static_cast<OccupancyGrid *>(g); }
+// info = {width, height, width step}; offset = world position of cell (0,0)
+void kref_occupancy_info(void * gp, int info[3], double offset[2])
+{
+  OccupancyGrid * g = static_cast<OccupancyGrid *>(gp);
+  info[0] = g->GetWidth(); info[1] = g->GetHeight(); info[2] = g->GetWidthStep();
+  offset[0] = g->GetCoordinateConverter()->GetOffset().GetX();
+  offset[1] = g->GetCoordinateConverter()->GetOffset().GetY();
+}
+// cells (width step x height bytes) and, if not NULL, the pass / hit counters (same layout)
+void kref_occupancy_copy(void * gp, uint8_t * cells, uint32_t * pass, uint32_t * hits)
+{
+  OccupancyGrid * g = static_cast<OccupancyGrid *>(gp);
+  const size_t n = static_cast<size_t>(g->GetDataSize());
+  if (cells) std::memcpy(cells, g->GetDataPointer(), n);
+  if (pass) std::memcpy(pass, g->GetCellPassCounts()->GetDataPointer(), n * sizeof(uint32_t));
+  if (hits) std::memcpy(hits, g->GetCellHitsCounts()->GetDataPointer(), n * sizeof(uint32_t));
+}
+
 }  // extern "C"

@@ -58,6 +58,15 @@ class PgOpts(C.Structure):
                 ("loss_function", C.c_int32), ("loss_scale", C.c_double)]
 
 
+class OgParams(C.Structure):
+    _fields_ = [("resolution", C.c_double), ("range_threshold", C.c_double), ("minimum_range", C.c_double),
+                ("maximum_range", C.c_double), ("min_pass_through", C.c_uint32), ("occupancy_threshold", C.c_double)]
+
+
+class OgInfo(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("stride", C.c_int32), ("offset", C.c_double * 2)]
+
+
 class PgSummary(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("successful_steps", C.c_int32), ("pcg_iterations", C.c_int32),
                 ("termination", C.c_int32), ("usable", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
@@ -120,6 +129,21 @@ def lib():
         L.b200pg_num_edges.argtypes = [C.c_void_p]
         L.b200pg_solve.argtypes = [C.c_void_p, C.POINTER(PgSummary)]
         L.b200pg_get_corrections.argtypes = [C.c_void_p, _IP, _DP, C.c_int32]
+    L.b200og_default_params.argtypes = [C.POINTER(OgParams)]
+    L.b200og_create.argtypes = [C.POINTER(OgParams), C.POINTER(C.c_void_p)]
+    L.b200og_destroy.argtypes = [C.c_void_p]
+    L.b200og_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200og_add_scans.argtypes = [C.c_void_p, C.POINTER(CScan), C.c_int32]
+    L.b200og_clear_scans.argtypes = [C.c_void_p]
+    L.b200og_num_scans.argtypes = [C.c_void_p]
+    L.b200og_build.argtypes = [C.c_void_p, C.POINTER(OgInfo)]
+    L.b200og_fetch.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.b200og_fetch_nav.argtypes = [C.c_void_p, C.POINTER(C.c_int8)]
+    L.b200og_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.b200og_launch_count.restype = C.c_int64
+    L.b200og_launch_count.argtypes = [C.c_void_p]
+    L.b200og_create_from_scans.argtypes = [C.POINTER(OgParams), C.POINTER(CScan), C.c_int32, C.POINTER(OgInfo),
+                                           C.POINTER(C.c_void_p)]
     _lib = L
     return L
 
@@ -453,3 +477,105 @@ class ScanSolver:
 
     def num_edges(self):
         return lib().b200pg_num_edges(self._h)
+
+
+GridStates_Unknown, GridStates_Occupied, GridStates_Free = 0, 100, 255   # Karto.h:4379-4381
+
+
+class OccupancyGrid:
+    """karto::OccupancyGrid (Karto.h:5883-6330) on the GPU: the map slam_toolbox publishes
+    (SMapper::getOccupancyGrid, src/slam_mapper.cpp:63-69).
+
+        grid = OccupancyGrid.CreateFromScans(scans, resolution)       # None for no scans, like the reference's NULL
+        grid.GetWidth(), grid.GetHeight(), grid.GetOffset(), grid.GetData() ...
+
+    or, keeping the scans resident in HBM between map updates:
+
+        grid = OccupancyGrid(resolution, laser); grid.AddScans(block); grid.Build(); grid.AddScans(more); grid.Build()
+    """
+
+    def __init__(self, resolution: float, laser: LaserRangeFinder | None = None, min_pass_through: int = 2,
+                 occupancy_threshold: float = 0.1):
+        laser = laser or LaserRangeFinder()
+        self.params = OgParams(resolution, laser.range_threshold, laser.minimum_range, laser.maximum_range,
+                               min_pass_through, occupancy_threshold)
+        self._h = C.c_void_p()
+        self.info = OgInfo()
+        _check(lib().b200og_create(C.byref(self.params), C.byref(self._h)))
+
+    @staticmethod
+    def CreateFromScans(rScans: ScanBlock | None, resolution: float, min_pass_through: int = 2,
+                        occupancy_threshold: float = 0.1) -> "OccupancyGrid | None":
+        if rScans is None or len(rScans) == 0:
+            return None
+        g = OccupancyGrid(resolution, rScans.laser, min_pass_through, occupancy_threshold)
+        g.AddScans(rScans)
+        g.Build()
+        return g
+
+    def close(self):
+        if self._h:
+            lib().b200og_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        _check(lib().b200og_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def AddScans(self, scans: ScanBlock):
+        _check(lib().b200og_add_scans(self._h, scans.c, len(scans)))
+
+    def ClearScans(self):
+        _check(lib().b200og_clear_scans(self._h))
+
+    def NumScans(self) -> int:
+        return lib().b200og_num_scans(self._h)
+
+    def Build(self):
+        _check(lib().b200og_build(self._h, C.byref(self.info)))
+        return self
+
+    def GetWidth(self) -> int:
+        return self.info.width
+
+    def GetHeight(self) -> int:
+        return self.info.height
+
+    def GetWidthStep(self) -> int:
+        return self.info.stride
+
+    def GetOffset(self) -> np.ndarray:
+        return np.array([self.info.offset[0], self.info.offset[1]])
+
+    def GetResolution(self) -> float:
+        return self.params.resolution
+
+    def GetData(self, counters: bool = False):
+        """cells [height, width step] uint8 (GridStates_*); with counters=True also (pass, hits) uint32."""
+        h, st = self.info.height, self.info.stride
+        cells = np.zeros((h, st), dtype=np.uint8)
+        ps = np.zeros((h, st), dtype=np.uint32) if counters else None
+        ht = np.zeros((h, st), dtype=np.uint32) if counters else None
+        _check(lib().b200og_fetch(self._h, cells.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                  ps.ctypes.data_as(C.POINTER(C.c_uint32)) if counters else None,
+                                  ht.ctypes.data_as(C.POINTER(C.c_uint32)) if counters else None))
+        return (cells, ps, ht) if counters else cells
+
+    def toNavMap(self) -> np.ndarray:
+        """vis_utils::toNavMap: [height, width] int8 with -1 unknown / 100 occupied / 0 free."""
+        out = np.zeros((self.info.height, self.info.width), dtype=np.int8)
+        _check(lib().b200og_fetch_nav(self._h, out.ctypes.data_as(C.POINTER(C.c_int8))))
+        return out
+
+    def kernel_ms(self) -> float:
+        ms = C.c_float()
+        _check(lib().b200og_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return lib().b200og_launch_count(self._h)

@@ -23,6 +23,7 @@ UNITS = {
     "sm_sweep.cu": ["-fmad=false"],
     "sm_sweep_fast.cu": ["-fmad=false"],
     "pose_graph.cu": [],
+    "occupancy.cu": ["-fmad=false"],
 }
 
 

@@ -211,6 +211,28 @@ def make_sequential_case(seed: int, buffer_len: int = 10, odo_xy: float = 0.03, 
                 query_pose=qpose, query_true=qtrue)
 
 
+def make_mapping_run(seed: int, n_scans: int = 24, step: float = 0.5, inf_frac: float = 0.02, nan_frac: float = 0.005,
+                     odd_readings: bool = True, world: World | None = None):
+    """Input of the map-publish step (OccupancyGrid::CreateFromScans over all processed scans): a trajectory of
+    n_scans sensor poses `step` apart with their scans.  odd_readings sprinkles the values AddScan treats specially
+    (Karto.h:6158-6171): below the minimum range, at / beyond the maximum range, exactly at the range threshold."""
+    rng = np.random.default_rng(seed)
+    world = world or make_world(seed)
+    poses = chain_poses(world, free_pose(world, rng), n_scans, rng, step=step)
+    ranges = noisy(raycast(world, poses), rng, inf_frac=inf_frac, nan_frac=nan_frac)
+    if odd_readings and ranges.size:
+        m = ranges.shape[1]
+        for s in range(len(ranges)):
+            k = rng.integers(0, m, 6)
+            ranges[s, k[0]] = 0.05
+            ranges[s, k[1]] = 0.1          # == minimum range: ignored (<=)
+            ranges[s, k[2]] = 30.0         # == maximum range: ignored (>=)
+            ranges[s, k[3]] = 12.0         # == range threshold: traced, no hit
+            ranges[s, k[4]] = 12.0 - 5e-7  # inside the KT_TOLERANCE band: traced to the end point, no hit
+            ranges[s, k[5]] = 25.0         # beyond the threshold: traced up to it
+    return dict(world=world, ranges=ranges, poses=poses)
+
+
 def wrap(a):
     """[-pi, pi) like solvers/ceres_utils.h:27-32 NormalizeAngle."""
     a = np.asarray(a, dtype=np.float64)

@@ -60,14 +60,29 @@ def ref_scans(ranges, poses, uid0=0):
     return [R.RefScan(r, p, uid0 + i) for i, (r, p) in enumerate(zip(np.atleast_2d(ranges), np.atleast_2d(poses)))]
 
 
-def gpu_block(ranges, poses):
-    from slam_toolbox_b200 import api
-    return api.ScanBlock(ranges, poses, api.LaserRangeFinder())
-
-
 def coarse_search(grid):
     """(searchSpaceOffset, searchSpaceResolution) of MatchScan's coarse pass (Mapper.cpp:577-585)."""
     side = math.floor(grid[0] / grid[1] + 0.5) + 1
     res = 1.0 / (1.0 / grid[1])
     off = 0.5 * (side - 1) * res
     return (off, off), (2 * res, 2 * res)
+
+
+def gpu_block(ranges, poses, range_threshold=None):
+    from slam_toolbox_b200 import api
+    laser = api.LaserRangeFinder(minimum_angle=LASER["min_angle"], maximum_angle=LASER["max_angle"], angular_resolution=LASER["ang_res"],
+                                 minimum_range=LASER["min_range"], maximum_range=LASER["max_range"],
+                                 range_threshold=LASER["range_threshold"] if range_threshold is None else range_threshold)
+    return api.ScanBlock(ranges, poses, laser)
+
+
+def assert_occupancy_equals_golden(g, z, name):
+    """g = dict(width, height, stride, offset, cells, passes, hits) vs tests/golden/occupancy_golden.npz case `name`"""
+    import hashlib
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()   # noqa: E731
+    assert [g["width"], g["height"], g["stride"]] == list(z[f"{name}/dims"])
+    assert np.array_equal(g["offset"], z[f"{name}/offset"])
+    assert np.array_equal(g["cells"], z[f"{name}/cells"])
+    assert [int(g["passes"].sum()), int(g["hits"].sum())] == list(z[f"{name}/sums"])
+    assert sha(g["passes"].astype(np.uint32)) == z[f"{name}/pass_sha"][0]
+    assert sha(g["hits"].astype(np.uint32)) == z[f"{name}/hits_sha"][0]

@@ -42,7 +42,8 @@ def available() -> bool:
     return os.path.exists(library("ref")) and os.path.exists(library("b200"))
 
 
-def run_inprocess(which: str, ranges: np.ndarray, odom: np.ndarray, params: dict, laser: dict, use_solver: bool = True):
+def run_inprocess(which: str, ranges: np.ndarray, odom: np.ndarray, params: dict, laser: dict, use_solver: bool = True,
+                  map_resolution: float = 0.0):
     L = C.CDLL(library(which))
     L.krep_create.restype = C.c_void_p
     L.krep_create.argtypes = [C.c_int]
@@ -73,11 +74,28 @@ def run_inprocess(which: str, ranges: np.ndarray, odom: np.ndarray, params: dict
     if which == "b200":
         L.b200_shim_match_calls.restype = C.c_long
         matches = int(L.b200_shim_match_calls())
-    return dict(poses=poses, kept=np.array(kept), process_seconds=st[0], solver_computes=int(st[1]), solver_ms=st[2],
-                edges=int(st[3]), scans=int(st[4]), match_calls=matches)
+    out = dict(poses=poses, kept=np.array(kept), process_seconds=st[0], solver_computes=int(st[1]), solver_ms=st[2],
+               edges=int(st[3]), scans=int(st[4]), match_calls=matches)
+    if map_resolution:
+        # the map-publish step over all processed scans: reference CPU build and the b200og binding, same process
+        L.krep_occupancy.restype = C.c_double
+        L.krep_occupancy.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_int), _DP, C.POINTER(C.c_uint8), C.c_long]
+        for tag, gpu in (("cpu", 0), ("gpu", 1)):
+            info = (C.c_int * 3)()
+            off = np.zeros(2)
+            sec = L.krep_occupancy(h, map_resolution, gpu, info, off.ctypes.data_as(_DP), None, 0)   # sizes (and warm-up)
+            cells = np.zeros((max(info[1], 0), max(info[2], 0)), dtype=np.uint8)
+            if sec >= 0:
+                sec = L.krep_occupancy(h, map_resolution, gpu, info, off.ctypes.data_as(_DP), cells.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                       cells.size)
+            out[f"map_{tag}_seconds"] = sec
+            out[f"map_{tag}_dims"] = np.array([info[0], info[1], info[2]])
+            out[f"map_{tag}_offset"] = off
+            out[f"map_{tag}_cells"] = cells
+    return out
 
 
-def run(which: str, ranges, odom, params=None, laser=None, use_solver=True, tmpdir=None):
+def run(which: str, ranges, odom, params=None, laser=None, use_solver=True, tmpdir=None, map_resolution=0.0):
     """Runs the replay in a fresh process and returns its result dict."""
     import tempfile
     params = params or YAML_PARAMS
@@ -86,7 +104,8 @@ def run(which: str, ranges, odom, params=None, laser=None, use_solver=True, tmpd
     d = tmpdir or tempfile.mkdtemp(prefix="replay_")
     fin, fout = os.path.join(d, f"in_{which}.npz"), os.path.join(d, f"out_{which}.npz")
     np.savez(fin, ranges=ranges, odom=odom, pkeys=np.array(list(params.keys())), pvals=np.array(list(params.values()), dtype=np.float64),
-             lkeys=np.array(list(laser.keys())), lvals=np.array(list(laser.values()), dtype=np.float64), use_solver=int(use_solver))
+             lkeys=np.array(list(laser.keys())), lvals=np.array(list(laser.values()), dtype=np.float64), use_solver=int(use_solver),
+             map_resolution=float(map_resolution))
     env = dict(os.environ)
     r = subprocess.run([sys.executable, os.path.abspath(__file__), which, fin, fout], capture_output=True, text=True, env=env)
     if r.returncode != 0:
@@ -123,7 +142,7 @@ if __name__ == "__main__":
     saved = os.dup(1)
     os.dup2(devnull, 1)   # the reference prints progress to stdout
     try:
-        out = run_inprocess(which, z["ranges"], z["odom"], params, laser, bool(int(z["use_solver"])))
+        out = run_inprocess(which, z["ranges"], z["odom"], params, laser, bool(int(z["use_solver"])), float(z["map_resolution"]))
     finally:
         os.dup2(saved, 1)
     np.savez(fout, **out)

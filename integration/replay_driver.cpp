@@ -11,6 +11,7 @@
 
 #include "karto_sdk/Mapper.h"
 #include "b200_solver.hpp"
+#include "occupancy_b200.hpp"
 
 using namespace karto;
 
@@ -138,6 +139,25 @@ void krep_stats(void * rp, double out[5])
   out[2] = r->solver ? r->solver->solve_ms() : 0;
   out[3] = static_cast<double>(r->mapper.GetGraph() ? r->mapper.GetGraph()->GetEdges().size() : 0);
   out[4] = static_cast<double>(r->scans.size());
+}
+
+// map publish over all processed scans (SMapper::getOccupancyGrid, src/slam_mapper.cpp:63-69):
+// use_gpu = 0 the reference's OccupancyGrid::CreateFromScans, 1 the b200og binding.  info = {width, height,
+// width step}; cells (if not NULL, cap bytes) receives the grid bytes.  Returns wall seconds, < 0 on failure.
+double krep_occupancy(void * rp, double resolution, int use_gpu, int info[3], double offset[2], unsigned char * cells, long cap)
+{
+  Replay * r = static_cast<Replay *>(rp);
+  LocalizedRangeScanVector v(r->scans.begin(), r->scans.end());
+  auto t0 = std::chrono::steady_clock::now();
+  OccupancyGrid * g = use_gpu ? karto::b200::CreateOccupancyGridFromScans(v, resolution) : OccupancyGrid::CreateFromScans(v, resolution);
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (!g) return -1.0;
+  info[0] = g->GetWidth(); info[1] = g->GetHeight(); info[2] = g->GetWidthStep();
+  offset[0] = g->GetCoordinateConverter()->GetOffset().GetX();
+  offset[1] = g->GetCoordinateConverter()->GetOffset().GetY();
+  if (cells && cap >= static_cast<long>(g->GetDataSize())) std::memcpy(cells, g->GetDataPointer(), g->GetDataSize());
+  delete g;
+  return sec;
 }
 
 }  // extern "C"

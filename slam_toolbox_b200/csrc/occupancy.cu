@@ -199,7 +199,7 @@ struct GrowBuf {
     size_t want = std::max(n, cap + cap / 2) + 16;
     T * q = nullptr;
     B200_CUDA(cudaMalloc(reinterpret_cast<void **>(&q), want * sizeof(T)));
-    if (keep) B200_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (keep && p) B200_CUDA(cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
     if (p) { B200_CUDA(cudaStreamSynchronize(st)); cudaFree(p); }
     p = q;
     cap = want;
@@ -321,7 +321,7 @@ int add_scans(b200og * h, const b200_scan * scans, int32_t n)
   h->d_ranges.ensure(old_beams + add, old_beams, h->stream);
   h->d_points.ensure(2 * (old_beams + add), 2 * old_beams, h->stream);
   h->d_sensor.ensure(2 * (old_scans + n), 2 * old_scans, h->stream);
-  h->d_start.ensure(old_scans + n + 1, old_scans + 1, h->stream);
+  h->d_start.ensure(old_scans + n + 1, old_scans, h->stream);   // entry old_scans is rewritten below
   upload_rows(h, scans, n, h->d_ranges.p + old_beams, 1, [](const b200_scan & s) { return s.ranges; });
   upload_rows(h, scans, n, h->d_points.p + 2 * old_beams, 2, [](const b200_scan & s) { return s.points_xy; });
   // sensor positions + prefix of beam counts: small, staged in the first pinned half

@@ -19,12 +19,16 @@ def test_mapper_process_replay_is_identical_with_the_gpu_matcher():
     ranges, odom, truth = replay.make_trajectory(4, 120)
     params = dict(replay.YAML_PARAMS, correlation_search_space_smear_deviation=0.03, loop_search_space_dimension=4.0)
     a = replay.run("ref", ranges, odom, params)
-    b = replay.run("b200", ranges, odom, params)
+    b = replay.run("b200", ranges, odom, params, map_resolution=0.05)
     assert a["scans"] == b["scans"] and a["scans"] > 50
     assert np.array_equal(a["kept"], b["kept"])
     assert a["edges"] == b["edges"] and a["solver_computes"] == b["solver_computes"]
     assert np.array_equal(a["poses"], b["poses"])
     assert b["match_calls"] >= b["scans"] - 1
+    # the published map (SMapper::getOccupancyGrid): b200og binding == the reference's OccupancyGrid::CreateFromScans
+    assert b["map_cpu_seconds"] >= 0 and b["map_gpu_seconds"] >= 0
+    assert np.array_equal(b["map_cpu_dims"], b["map_gpu_dims"]) and np.array_equal(b["map_cpu_offset"], b["map_gpu_offset"])
+    assert np.array_equal(b["map_cpu_cells"], b["map_gpu_cells"]) and (b["map_gpu_cells"] == 100).sum() > 100
     # the matcher actually corrected the drifting odometry
     kept = a["kept"]
     err_odo = np.abs(odom[kept, :2] - truth[kept, :2]).max()

@@ -1,5 +1,5 @@
 /* ORACLE / TEST INFRASTRUCTURE -- plain-C restatement of the reference's correlative scan
- * matcher (karto::ScanMatcher, /root/reference/lib/karto_sdk/src/Mapper.cpp:477-1208 and the
+ * matcher and occupancy grid (karto::OccupancyGrid::CreateFromScans, Karto.h:5946-6274; karto::ScanMatcher, /root/reference/lib/karto_sdk/src/Mapper.cpp:477-1208 and the
  * Karto.h/Mapper.h types it uses).  Only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs may load this; the product library never does.
  *

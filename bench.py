@@ -320,7 +320,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from slam_toolbox_b200 import api
+    from slam_toolbox_b200 import api, sweep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the b200 implementation has no CPU fallback")
@@ -348,6 +348,9 @@ def main():
     queries = api.ScanBlock(qr, qp, laser)
     npairs = N_QUERY * n_cand
     keys = torch.zeros(N_QUERY, dtype=torch.int64, device="cuda")
+    pair_q = np.repeat(np.arange(N_QUERY), n_cand)                       # pairs are query-major when no pair list is given
+    pair_c_global = np.tile(np.arange(n_cand), N_QUERY) + rank * n_cand
+    winners = None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -406,11 +409,21 @@ def main():
         if world > 1:
             sm.batch_reduce_keys(keys.data_ptr(), rank * n_cand)
             dist.all_reduce(keys, op=dist.ReduceOp.MAX)
-            torch.cuda.synchronize()
+            # winners exchange: the owner of each query's best candidate contributes (response, mean, cov)
+            tab = torch.from_numpy(sweep.winners_payload(keys.cpu().numpy(), rank * n_cand, (rank + 1) * n_cand, pair_q, pair_c_global,
+                                                          r_e2e[0], r_e2e[1], r_e2e[2])).cuda()
+            sweep.allreduce_winners(tab)
+            winners = tab.cpu().numpy()
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d, d2h = sm.transfer_bytes()
     assert np.array_equal(r_e2e[0], resp_dev)
+    if world > 1:   # every rank holds the same winner rows, and the owner's row is its own result
+        bs, gid = sweep.unpack_keys(keys.cpu().numpy())
+        for q in range(N_QUERY):
+            if rank * n_cand <= gid[q] < (rank + 1) * n_cand:
+                j = q * n_cand + int(gid[q]) - rank * n_cand
+                assert winners[q, 0] == r_e2e[0][j] and np.array_equal(winners[q, 1:4], r_e2e[1][j])
 
     # max over ranks
     t = torch.tensor([dev_ms, e2e_s * 1e3, last_kernel_ms], dtype=torch.float64, device="cuda")
@@ -467,7 +480,7 @@ def main():
         "config": {"workload": f"cfg2 loop-closure batch: {N_QUERY} query x {n_cand} candidate chains (chain length {chain_len}) of "
                                f"1081-beam scans per GPU, +-2m/+-20deg window, candidates sharded over {world} GPU(s)",
                    "search": f"41x41x{n_angles} poses", "grid": "565x568 u8 (res 0.05 m, smear 0.03 m, range threshold 12 m)",
-                   "l2": "L2 flushed between timed steps (256 MiB write)", "collective": "all_reduce(MAX) of packed best-response keys" if world > 1 else "none"},
+                   "l2": "L2 flushed between timed steps (256 MiB write)", "collective": "all_reduce(MAX) of packed best-response keys (+ all_reduce(SUM) of the winners' [Q,13] rows in the e2e leg)" if world > 1 else "none"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),

@@ -21,7 +21,6 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 UNITS = {
     "scan_matcher.cu": ["-fmad=false"],
     "sm_sweep.cu": ["-fmad=false"],
-    "sm_sweep_fast.cu": ["-fmad=false"],
     "pose_graph.cu": [],
     "occupancy.cu": ["-fmad=false"],
 }
@@ -43,8 +42,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
     rebuilt = False
     for unit, extra in UNITS.items():
         src = os.path.join(CSRC, unit)
-        if not os.path.exists(src):
-            continue
         obj = os.path.join(LIBDIR, unit.replace(".cu", ".o"))
         objs.append(obj)
         if force or _newer(src, obj):

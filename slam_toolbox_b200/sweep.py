@@ -8,6 +8,12 @@ collective; the only exchange is ONE all-reduce(MAX) of a packed 64-bit key per 
 
 MAX picks the highest sum and, between equal sums, the LOWEST candidate id -- deterministic for any
 rank count.  The same packing is produced on the device by b200sm_batch_reduce_keys.
+
+The winners' results follow in a second, equally small exchange: the rank that owns the winning candidate
+of a query contributes its (response, mean[3], cov[9]) row, every other rank contributes zeros, and one
+all-reduce(SUM) of the [Q, 13] table leaves the row on every rank -- x + 0 is exact, so the values are the
+owner's bits.  Per-candidate results stay on their owners (TryCloseLoop consumes every passing chain,
+Mapper.cpp:1500-1561) and come back through b200sm_batch_fetch.
 """
 from __future__ import annotations
 
@@ -45,3 +51,30 @@ def allreduce_best(keys_tensor):
     import torch.distributed as dist
     dist.all_reduce(keys_tensor, op=dist.ReduceOp.MAX)
     return keys_tensor
+
+
+def winners_payload(reduced_keys: np.ndarray, lo: int, hi: int, pair_query: np.ndarray, pair_global_chain: np.ndarray,
+                    response: np.ndarray, mean: np.ndarray, cov: np.ndarray) -> np.ndarray:
+    """[Q, 13] float64 table for the winners exchange: row q = (response, mean[3], cov[9]) of the pair (q, winning
+    candidate) if this rank owns that candidate (lo <= id < hi), else zeros.  reduced_keys = keys after all-reduce."""
+    _, gid = unpack_keys(reduced_keys)
+    nq = len(gid)
+    out = np.zeros((nq, 13), dtype=np.float64)
+    pq = np.asarray(pair_query, dtype=np.int64)
+    pc = np.asarray(pair_global_chain, dtype=np.int64)
+    cov = np.asarray(cov, dtype=np.float64).reshape(len(pq), 9)
+    own = (gid >= lo) & (gid < hi) & (np.asarray(reduced_keys) != 0)
+    if own.any():
+        hit = np.nonzero(own[pq] & (pc == gid[pq]))[0]     # the pairs that are some query's winner
+        q = pq[hit]
+        out[q, 0] = np.asarray(response, dtype=np.float64)[hit]
+        out[q, 1:4] = np.asarray(mean, dtype=np.float64)[hit]
+        out[q, 4:13] = cov[hit]
+    return out
+
+
+def allreduce_winners(table_tensor):
+    """In-place all-reduce(SUM) of the [Q, 13] winners table (torch float64) over the default process group."""
+    import torch.distributed as dist
+    dist.all_reduce(table_tensor, op=dist.ReduceOp.SUM)
+    return table_tensor

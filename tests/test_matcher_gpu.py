@@ -214,14 +214,24 @@ def test_sharded_sweep_keys_equal_the_unsharded_reduction():
         gm.batch_reduce_keys(k.data_ptr(), offset)
         torch.cuda.synchronize()
         sums, _, _ = gm.batch_best()
-        return k, sums.reshape(Q, hi - lo)
+        return k, sums.reshape(Q, hi - lo), gm.batch_fetch()
 
-    full, sums = keys_for(0, Cn, 0)
-    parts = []
+    full, sums, (resp, mean, cov) = keys_for(0, Cn, 0)
+    parts, results, ranges = [], [], []
     for r in range(3):
         lo, hi = sweep.shard_range(Cn, 3, r)
-        parts.append(keys_for(lo, hi, lo)[0])
+        k, _, res = keys_for(lo, hi, lo)
+        parts.append(k); results.append(res); ranges.append((lo, hi))
     merged = torch.maximum(torch.maximum(parts[0], parts[1]), parts[2])
     assert torch.equal(merged, full)
     s, g = sweep.unpack_keys(full.cpu().numpy())
     assert np.array_equal(s, sums.max(axis=1)) and np.array_equal(g, sums.argmax(axis=1))
+    # winners exchange: each "rank" contributes the rows it owns, the sum is the unsharded winner's result
+    table = np.zeros((Q, 13))
+    for (lo, hi), (rr, mm, cc) in zip(ranges, results):
+        pq = np.repeat(np.arange(Q), hi - lo)
+        pc = np.tile(np.arange(lo, hi), Q)
+        table += sweep.winners_payload(merged.cpu().numpy(), lo, hi, pq, pc, rr, mm, cc)
+    win = np.arange(Q) * Cn + g
+    assert np.array_equal(table[:, 0], resp[win]) and np.array_equal(table[:, 1:4], mean[win])
+    assert np.array_equal(table[:, 4:], cov[win].reshape(Q, 9))

@@ -54,6 +54,13 @@ def _worker(rank, world, port, n_queries, n_cand, seed):
     s, g = sweep.unpack_keys(keys.numpy())
     assert np.array_equal(s, sums.max(axis=1))
     assert np.array_equal(g, sums.argmax(axis=1))           # argmax = first (lowest id) maximum
+    # winners exchange: the owner's (response, mean, cov) row reaches every rank unchanged
+    full = np.random.default_rng(seed + 1).normal(size=(n_queries, n_cand, 13))
+    mine = full[:, lo:hi].reshape(-1, 13)
+    tab = torch.from_numpy(sweep.winners_payload(keys.numpy(), lo, hi, pq, gid, mine[:, 0], mine[:, 1:4], mine[:, 4:]))
+    assert int((tab.numpy()[:, 0] != 0).sum()) == int(((g >= lo) & (g < hi)).sum())
+    sweep.allreduce_winners(tab)
+    assert np.array_equal(tab.numpy(), full[np.arange(n_queries), g])
     dist.barrier()
     dist.destroy_process_group()
 

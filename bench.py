@@ -267,7 +267,7 @@ def occupancy_bench(steps: int, with_cpu: bool):
     launches = g.launch_count()
     g.close()
     e2e = []
-    for _ in range(2):                           # through the public one-shot call: H2D of all scans + build + cells D2H
+    for _ in range(3):                           # through the public one-shot call: H2D of all scans + build + cells D2H
         t = time.perf_counter()
         g2 = api.OccupancyGrid.CreateFromScans(blk, res)
         c2 = g2.GetData()

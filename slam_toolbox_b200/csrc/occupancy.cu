@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <vector>
 
@@ -220,7 +221,7 @@ struct b200og {
   std::vector<int32_t> start{0};
   int32_t maxbeams = 0;
   // staging (two pinned halves, filled while the other one is in flight)
-  PinBuf<double> stage[2];
+  double * stage[2] = {nullptr, nullptr};
   cudaEvent_t stage_done[2] = {nullptr, nullptr};
   // build state
   DevBuf<uint32_t> d_pass, d_hits;
@@ -255,6 +256,35 @@ namespace {
 
 constexpr size_t kStageDoubles = (size_t)1 << 20;   // 8 MB per pinned half
 
+// Pinned staging halves are kept for the life of the process (cudaMallocHost of 16 MB costs milliseconds, which the
+// one-shot b200og_create_from_scans would pay on every map update). A handle borrows a pair and returns it.
+struct StagePool {
+  std::mutex m;
+  std::vector<double *> free_list;
+  double * take()
+  {
+    {
+      std::lock_guard<std::mutex> g(m);
+      if (!free_list.empty()) { double * p = free_list.back(); free_list.pop_back(); return p; }
+    }
+    double * p = nullptr;
+    B200_CUDA(cudaMallocHost(reinterpret_cast<void **>(&p), kStageDoubles * sizeof(double)));
+    return p;
+  }
+  void give(double * p)
+  {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(m);
+    if (free_list.size() < 4) { free_list.push_back(p); return; }
+    cudaFreeHost(p);
+  }
+};
+StagePool & stage_pool()
+{
+  static StagePool * pool = new StagePool();   // never destroyed: no cudaFreeHost after the runtime is gone
+  return *pool;
+}
+
 bool params_ok(const b200og_params & p)
 {
   if (!(p.resolution == p.resolution) || double_equal(p.resolution, 0.0)) {   // Karto.h:5916-5918 throws
@@ -278,7 +308,7 @@ void upload_rows(b200og * h, const b200_scan * scans, int32_t n, double * dst, i
   bool pending[2] = {false, false};
   auto flush = [&]() {
     if (!fill) return;
-    B200_CUDA(cudaMemcpyAsync(dst + sent, h->stage[half].p, fill * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    B200_CUDA(cudaMemcpyAsync(dst + sent, h->stage[half], fill * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     B200_CUDA(cudaEventRecord(h->stage_done[half], h->stream));
     pending[half] = true;
     sent += fill;
@@ -291,7 +321,7 @@ void upload_rows(b200og * h, const b200_scan * scans, int32_t n, double * dst, i
     size_t left = (size_t)scans[s].n * per_beam;
     while (left) {
       const size_t take = std::min(left, kStageDoubles - fill);
-      std::memcpy(h->stage[half].p + fill, src, take * sizeof(double));
+      std::memcpy(h->stage[half] + fill, src, take * sizeof(double));
       fill += take; src += take; left -= take;
       if (fill == kStageDoubles) flush();
     }
@@ -316,8 +346,8 @@ int add_scans(b200og * h, const b200_scan * scans, int32_t n)
   if (old_beams + add > (size_t)INT32_MAX) { set_last_error("b200og: more than 2^31-1 beams in the scan store"); return B200_ERR_UNSUPPORTED; }
   if (n == 0) return B200_OK;
   h->ensure_stream();
-  h->stage[0].reserve(kStageDoubles);
-  h->stage[1].reserve(kStageDoubles);
+  for (auto & sp : h->stage)
+    if (!sp) sp = stage_pool().take();
   h->d_ranges.ensure(old_beams + add, old_beams, h->stream);
   h->d_points.ensure(2 * (old_beams + add), 2 * old_beams, h->stream);
   h->d_sensor.ensure(2 * (old_scans + n), 2 * old_scans, h->stream);
@@ -325,7 +355,7 @@ int add_scans(b200og * h, const b200_scan * scans, int32_t n)
   upload_rows(h, scans, n, h->d_ranges.p + old_beams, 1, [](const b200_scan & s) { return s.ranges; });
   upload_rows(h, scans, n, h->d_points.p + 2 * old_beams, 2, [](const b200_scan & s) { return s.points_xy; });
   // sensor positions + prefix of beam counts: small, staged in the first pinned half
-  double * sp = h->stage[0].p;
+  double * sp = h->stage[0];
   std::vector<int32_t> st(n + 1);
   st[0] = (int32_t)old_beams;
   for (int32_t s = 0; s < n; ++s) {
@@ -468,6 +498,7 @@ void b200og_destroy(b200og * h)
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); }
   for (auto & e : h->stage_done) if (e) cudaEventDestroy(e);
+  for (auto & sp : h->stage) { stage_pool().give(sp); sp = nullptr; }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

@@ -10,12 +10,12 @@
 //
 // Kernels of one build (b200og_build):
 //   k_og_bbox    min / max over the sensor positions and the in-range points   (ComputeDimensions)
-//   k_og_trace   one WARP per beam: lane l visits cells l, l+32, ... of the Bresenham line, whose
-//                y at step k has the closed form y0 + ystep * floor((2 k dY + dX) / (2 dX));
-//                counters are bumped with RED.ADD (no return value) -- integer sums commute, so the
+//   k_og_trace   a warp takes 32 adjacent beams of a scan, one per lane, and runs the reference's integer
+//                Bresenham loop on them in lock step; equal cell indices of neighbouring lanes are merged
+//                into one RED.ADD of the run length (no return value) -- integer sums commute, so the
 //                result does not depend on the order and equals the reference's sequential loop
 //   k_og_update  counters -> cell state (UpdateCell Karto.h:6241-6254), FP64 ratio test as the reference
-// Beams of DIFFERENT scans are interleaved over the warps so that the cells next to one sensor
+// Beam groups of DIFFERENT scans are interleaved over the warps so that the cells next to one sensor
 // (which every beam of that scan crosses) are not hammered by the whole grid at the same time.
 //
 // Compiled with -fmad=false: the clipped end point sx + ratio * dx and (w - offset) * scale must
@@ -106,54 +106,89 @@ __global__ void __launch_bounds__(kOgThreads) k_og_bbox(OgDev d, double * partia
   }
 }
 
-// AddScan (Karto.h:6139-6182) + RayTrace (:6193-6229) + TraceLine (:4874-4927), one warp per beam.
+// AddScan (Karto.h:6139-6182) + RayTrace (:6193-6229) + TraceLine (:4874-4927).
+// A warp takes 32 ADJACENT beams of one scan: every lane prepares its beam (the FP64 part: skip / clip rules, the
+// four world->grid conversions, the steep / direction swaps) and then runs the reference's own integer loop on it,
+// all lanes in lock step.  Adjacent beams of a scan cross the same cells for most of their length (all 32 within
+// ~7 cells of the sensor, still ~4 per cell at 55 cells), so before touching memory the warp merges runs of equal
+// cell indices: one RED.ADD of the run length per distinct cell instead of one per lane.  Counter updates are the
+// kernel's bound (REDG issues at ~1.3 cycles per LANE per SM, and equal addresses serialise in L2), so this is the
+// main lever; sums of integers commute, so the counters still equal the reference's.
+// key = cell index (< 2^31: b200og_build refuses larger grids), -1 when this lane has nothing to add
+__device__ __forceinline__ void og_merged_add(uint32_t * __restrict__ base, int32_t key, bool valid, int lane, uint32_t * __restrict__ base2)
+{
+  const int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool leader = valid && (lane == 0 || key != prev);
+  const uint32_t bounds = __ballot_sync(0xffffffffu, leader || !valid);
+  if (leader) {
+    const uint32_t above = lane == 31 ? 0u : (bounds & (0xFFFFFFFEu << lane));
+    const uint32_t count = (above ? (uint32_t)__ffs(above) - 1u : 32u) - (uint32_t)lane;
+    atomicAdd(base + key, count);
+    if (base2) atomicAdd(base2 + key, count);
+  }
+}
+
 __global__ void __launch_bounds__(kOgThreads) k_og_trace(OgDev d)
 {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (kOgThreads / 32);
-  const int64_t total = (int64_t)d.nscans * d.maxbeams;
+  const int32_t groups_per_scan = (d.maxbeams + 31) / 32;
+  const int64_t total = (int64_t)d.nscans * groups_per_scan;
+  // consecutive warps take groups of DIFFERENT scans, so that the cells around one sensor are not hit by the whole grid at once
   for (int64_t g = (int64_t)blockIdx.x * (kOgThreads / 32) + (threadIdx.x >> 5); g < total; g += nwarps) {
-    const int32_t scan = (int32_t)(g % d.nscans), beam = (int32_t)(g / d.nscans);
+    const int32_t scan = (int32_t)(g % d.nscans), beam = (int32_t)(g / d.nscans) * 32 + lane;
     const int32_t b0 = d.start[scan];
-    if (beam >= d.start[scan + 1] - b0) continue;
-    const int64_t i = (int64_t)b0 + beam;
-    const double r = d.ranges[i];
-    if (r <= d.minr || r >= d.maxr || r != r) continue;              // ignored readings, Karto.h:6160
-    const bool valid_end = r < (d.rt - kTolerance);                  // Karto.h:6158
-    const double sx = d.sensor[2 * scan], sy = d.sensor[2 * scan + 1];
-    double px = d.points[2 * i], py = d.points[2 * i + 1];
-    if (r >= d.rt) {                                                 // trace up to the range threshold, Karto.h:6164-6171
-      const double ratio = d.rt / r;
-      const double dx = px - sx, dy = py - sy;
-      px = sx + ratio * dx;
-      py = sy + ratio * dy;
+    int32_t x = 0, y = 0, dX = 0, dY = 0, ystep = 1, len = 0;
+    bool steep = false, end_hit = false;
+    int32_t end_key = -1;
+    if (beam < d.start[scan + 1] - b0) {
+      const int64_t i = (int64_t)b0 + beam;
+      const double r = d.ranges[i];
+      if (!(r <= d.minr || r >= d.maxr || r != r)) {                    // ignored readings, Karto.h:6160
+        const bool valid_end = r < (d.rt - kTolerance);                 // Karto.h:6158
+        const double sx = d.sensor[2 * scan], sy = d.sensor[2 * scan + 1];
+        double px = d.points[2 * i], py = d.points[2 * i + 1];
+        if (r >= d.rt) {                                                // trace up to the range threshold, Karto.h:6164-6171
+          const double ratio = d.rt / r;
+          const double dx = px - sx, dy = py - sy;
+          px = sx + ratio * dx;
+          py = sy + ratio * dy;
+        }
+        const int32_t fx = world_to_grid(sx, d.offx, d.scale), fy = world_to_grid(sy, d.offy, d.scale);
+        const int32_t tx = world_to_grid(px, d.offx, d.scale), ty = world_to_grid(py, d.offy, d.scale);
+        int64_t a0 = fx, c0 = fy, a1 = tx, c1 = ty;
+        steep = llabs(c1 - c0) > llabs(a1 - a0);                        // Karto.h:4876-4884
+        if (steep) { int64_t t = a0; a0 = c0; c0 = t; t = a1; a1 = c1; c1 = t; }
+        if (a0 > a1) { int64_t t = a0; a0 = a1; a1 = t; t = c0; c0 = c1; c1 = t; }
+        if (a1 - a0 >= kOgMaxCells) {
+          atomicExch(d.flag, 1);
+        } else {
+          x = (int32_t)a0; y = (int32_t)c0;
+          dX = (int32_t)(a1 - a0); dY = (int32_t)llabs(c1 - c0);
+          ystep = c0 < c1 ? 1 : -1;
+          len = dX + 1;
+          if (valid_end && is_up_to(tx, d.width) && is_up_to(ty, d.height)) {   // the end point, Karto.h:6212-6226
+            end_hit = true;
+            end_key = ty * d.stride + tx;
+          }
+        }
+      }
     }
-    const int32_t fx = world_to_grid(sx, d.offx, d.scale), fy = world_to_grid(sy, d.offy, d.scale);
-    const int32_t tx = world_to_grid(px, d.offx, d.scale), ty = world_to_grid(py, d.offy, d.scale);
-    int64_t x0 = fx, y0 = fy, x1 = tx, y1 = ty;
-    const bool steep = llabs(y1 - y0) > llabs(x1 - x0);
-    if (steep) { int64_t t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; }
-    if (x0 > x1) { int64_t t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
-    const int64_t dX = x1 - x0, dY = llabs(y1 - y0);
-    if (dX >= kOgMaxCells) {
-      if (lane == 0) atomicExch(d.flag, 1);
-      continue;
-    }
-    const int32_t ystep = y0 < y1 ? 1 : -1;
-    const uint32_t udX = (uint32_t)dX, udY = (uint32_t)dY, den = 2u * udX;
-    const bool narrow = udX < 32768u;   // 2 k dY + dX < 2^31: 32-bit division
-    for (uint32_t k = lane; k <= udX; k += 32) {
-      uint32_t n = 0;
-      if (udX) n = narrow ? (2u * k * udY + udX) / den : (uint32_t)((2ull * k * udY + udX) / (2ull * udX));
-      const int32_t x = (int32_t)x0 + (int32_t)k, y = (int32_t)y0 + ystep * (int32_t)n;
+    int32_t maxlen = len;
+    for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    int32_t error = 0;
+    for (int32_t step = 0; step < maxlen; ++step) {                     // TraceLine's loop, Karto.h:4900-4926
+      const bool active = step < len;
       const int32_t cx = steep ? y : x, cy = steep ? x : y;
-      if (is_up_to(cx, d.width) && is_up_to(cy, d.height)) atomicAdd(d.pass + (size_t)cy * d.stride + cx, 1u);
+      const bool valid = active && is_up_to(cx, d.width) && is_up_to(cy, d.height);
+      if (active) {
+        error += dY;
+        if (2 * error >= dX) { y += ystep; error -= dX; }
+        ++x;
+      }
+      og_merged_add(d.pass, valid ? cy * d.stride + cx : -1, valid, lane, nullptr);
     }
-    if (lane == 0 && valid_end && is_up_to(tx, d.width) && is_up_to(ty, d.height)) {   // Karto.h:6212-6226
-      const size_t c = (size_t)ty * d.stride + tx;
-      atomicAdd(d.pass + c, 1u);
-      atomicAdd(d.hits + c, 1u);
-    }
+    if (__any_sync(0xffffffffu, end_hit)) og_merged_add(d.pass, end_key, end_hit, lane, d.hits);
   }
 }
 

@@ -47,6 +47,14 @@ def test_argument_validation_needs_no_device():
     assert L.b200sm_create(None, C.byref(h)) == api.ERR_INVALID_ARG
     assert L.b200sm_match(None, None, None, 0, 0, 0, None, None, None) == api.ERR_INVALID_ARG
     assert L.b200pg_add_node(None, 0, None) == api.ERR_INVALID_ARG
+    og = api.OgParams()
+    L.b200og_default_params(C.byref(og))
+    assert (og.resolution, og.min_pass_through, og.occupancy_threshold) == (0.05, 2, 0.1)
+    og.resolution = 0.0                                                              # "Resolution cannot be 0", Karto.h:5916-5918
+    assert L.b200og_create(C.byref(og), C.byref(h)) == api.ERR_INVALID_ARG and b"Karto.h:5916" in L.b200_last_error()
+    assert L.b200og_create(None, C.byref(h)) == api.ERR_INVALID_ARG
+    assert L.b200og_add_scans(None, None, 0) == api.ERR_INVALID_ARG and L.b200og_build(None, None) == api.ERR_INVALID_ARG
+    assert L.b200og_num_scans(None) == 0
     o = api.PgOpts()
     L.b200pg_default_opts(C.byref(o))
     assert (o.max_num_iterations, o.function_tolerance, o.initial_trust_region_radius, o.jacobi_scaling) == (50, 1e-3, 1e4, 1)
@@ -75,3 +83,6 @@ def test_no_cpu_fallback_without_a_device():
     with pytest.raises(api.B200Error) as e:
         api.ScanSolver()
     assert e.value.code == api.ERR_CUDA
+    with pytest.raises(api.B200Error) as e:
+        api.OccupancyGrid(0.05)
+    assert e.value.code == api.ERR_CUDA and "no CPU fallback" in str(e.value)

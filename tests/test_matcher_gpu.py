@@ -235,3 +235,32 @@ def test_sharded_sweep_keys_equal_the_unsharded_reduction():
     win = np.arange(Q) * Cn + g
     assert np.array_equal(table[:, 0], resp[win]) and np.array_equal(table[:, 1:4], mean[win])
     assert np.array_equal(table[:, 4:], cov[win].reshape(Q, 9))
+
+
+@pytest.mark.parametrize("n_beams,angle_min_deg,inc_deg", [(360, -180.0, 1.0), (1440, -180.0, 0.25), (721, -90.0, 0.25), (50, -25.0, 1.0)])
+def test_other_lasers_single_and_batch(n_beams, angle_min_deg, inc_deg):
+    """Lasers other than the 1081-beam one of the BASELINE configs (a 360-beam 1-degree lidar, a 1440-beam full circle,
+    a 180-degree scanner, a 50-beam toy): single match (coarse + fine) and the batched sweep against the oracle."""
+    from oracle import karto_port as P
+    amin, ainc = np.radians(angle_min_deg), np.radians(inc_deg)
+    laser = api.LaserRangeFinder(minimum_angle=amin, maximum_angle=amin + (n_beams - 1) * ainc, angular_resolution=ainc)
+    rng = np.random.default_rng(n_beams)
+    world = synth.make_world(77)
+    qtrue = synth.free_pose(world, rng)
+    cposes = synth.poses_near(world, qtrue[:2], 2.0, 9, rng)
+    qpose = qtrue + np.array([0.2, -0.15, 0.05])
+    qr = synth.noisy(synth.raycast(world, qtrue, n_beams, amin, ainc), rng, inf_frac=0.02)
+    cr = synth.noisy(synth.raycast(world, cposes, n_beams, amin, ainc), rng, inf_frac=0.02)
+    pq = P.PortScan(qr[0], qpose, amin, ainc)
+    pc = [P.PortScan(r, p, amin, ainc) for r, p in zip(cr, cposes)]
+    gq, gc = api.ScanBlock(qr, qpose[None, :], laser), api.ScanBlock(cr, cposes, laser)
+    for mapper, grid, pen, refine in ((H.MAPPER_LOOP, H.GRID_LOOP, False, False), (H.MAPPER_SEQ, H.GRID_SEQ, True, True)):
+        pm, gm = H.port_matcher(mapper, grid), H.gpu_matcher(mapper, grid)
+        assert same(pm.match(pq, pc[:3], pen, refine), gm.MatchScan(gq, api.ScanBlock(cr[:3], cposes[:3], laser), pen, refine))
+    pm, gm = H.port_matcher(H.MAPPER_LOOP, H.GRID_LOOP), H.gpu_matcher(H.MAPPER_LOOP, H.GRID_LOOP)
+    chain_start = np.array([0, 1, 2, 3, 6, 9], dtype=np.int32)      # three single scans and two chains of three
+    exp = [pm.match(pq, pc[chain_start[c]:chain_start[c + 1]], False, False) for c in range(5)]
+    resp, mean, cov = gm.MatchScanBatch(gq, gc, chain_start, None, False, False)
+    for c in range(5):
+        assert same(exp[c], (resp[c], mean[c], cov[c])), c
+    assert gm.batch_info()["fast"]

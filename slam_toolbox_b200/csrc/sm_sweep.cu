@@ -25,40 +25,69 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------
 
 // ScanMatcher::FindValidPoints (M.cpp:1113-1164) + WorldToGrid + ROI test (M.cpp:1082-1088) for
-// every (pair, scan of its chain).  One WARP per scan: lanes load 32 points at a time (coalesced),
-// every lane then replays the sequential state machine on them through shuffles (identical state in
-// all lanes, no divergence); accepted index ranges set flags in shared memory.  A second, parallel
-// pass turns accepted points into grid cells and compacts the in-ROI ones in scan order.
-// cells[item * max_n + k] = gx | gy << 16 of the k-th point that lands inside the ROI.
+// every (pair, scan of its chain).  One WARP per scan, the scan's points staged in shared memory.
+// The reference walks the points one by one, but its state only changes at an ANCHOR: the first point
+// farther than 10 cm from the previous anchor (M.cpp:1138-1139).  So the warp tests 32 points against
+// the current anchor at once (the reference's own expression, evaluated per lane), a ballot finds the
+// next anchor, and the side test + range bookkeeping (M.cpp:1145-1160) run once per anchor instead of
+// once per point: ~4x fewer dependent steps at indoor point spacings.  Accepted index ranges set flags
+// in shared memory; a second, parallel pass turns accepted points into grid cells and compacts the
+// in-ROI ones in scan order.  cells[item * max_n + k] = gx | gy << 16 of the k-th point inside the ROI.
 constexpr int kFvWarps = 4;
+constexpr int kFvBytesPerPoint = 17;   // double2 + flag
 __global__ void __launch_bounds__(kFvWarps * 32) k_find_valid(SweepDev d)
 {
-  extern __shared__ unsigned char s_valid_all[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int item = blockIdx.x * kFvWarps + warp;
+  extern __shared__ __align__(16) unsigned char s_fv[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int item = blockIdx.x * nw + warp;
   if (item >= d.nitems) return;
-  unsigned char * valid = s_valid_all + (size_t)warp * d.max_n;
+  double2 * P = reinterpret_cast<double2 *>(s_fv) + (size_t)warp * d.max_n;
+  unsigned char * valid = s_fv + (size_t)nw * d.max_n * sizeof(double2) + (size_t)warp * d.max_n;
   const int pair = d.item_pair[item];
   const int scan = d.item_scan[item];
   const int q = d.pair_query[pair];
   const double vx = d.qgeom[q * 4 + 0], vy = d.qgeom[q * 4 + 1];
   const double ox = d.qgeom[q * 4 + 2], oy = d.qgeom[q * 4 + 3];
-  const double * pts = d.points + 2 * (size_t)d.scan_pt_start[scan];
+  const double2 * pts = reinterpret_cast<const double2 *>(d.points) + (size_t)d.scan_pt_start[scan];
   const int n = d.scan_pt_start[scan + 1] - d.scan_pt_start[scan];
-  for (int i = lane; i < n; i += 32) valid[i] = 0;
+  for (int i = lane; i < n; i += 32) { P[i] = pts[i]; valid[i] = 0; }
   __syncwarp();
-  ValidPointState st;
-  st.init();
+  // the first point without a NaN coordinate becomes the first anchor (M.cpp:1130-1133); until then
+  // firstPoint is (0, 0) and every distance test sees a NaN: nothing happens
+  int i = n;
   for (int base = 0; base < n; base += 32) {
-    const int mine = base + lane;
-    double px = 0.0, py = 0.0;
-    if (mine < n) { px = pts[2 * mine]; py = pts[2 * mine + 1]; }
-    const int cnt = min(32, n - base);
-    for (int k = 0; k < cnt; ++k) {
-      const double cx = __shfl_sync(0xffffffffu, px, k), cy = __shfl_sync(0xffffffffu, py, k);
-      int lo, hi;
-      st.step(base + k, cx, cy, vx, vy, lo, hi);
-      for (int t = lo + lane; t < hi; t += 32) valid[t] = 1;   // same range in every lane
+    const int t = base + lane;
+    bool ok = false;
+    if (t < n) { const double2 c = P[t]; ok = !(c.x != c.x) && !(c.y != c.y); }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m) { i = base + __ffs(m) - 1; break; }
+  }
+  if (i < n) {
+    double fx = P[i].x, fy = P[i].y;
+    int trailing = 0;
+    ++i;   // the anchor itself is at distance 0 (or NaN for an infinite point): no event
+    while (i < n) {
+      const int t = i + lane;
+      bool far = false;
+      if (t < n) {
+        const double2 c = P[t];
+        const double dx = fx - c.x, dy = fy - c.y;
+        far = dx * dx + dy * dy > 0.1 * 0.1;                  // delta.SquaredLength() > minSquareDistance
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, far);
+      if (!m) { i += 32; continue; }
+      const int idx = i + __ffs(m) - 1;
+      const double2 c = P[idx];
+      const double a = vy - fy;
+      const double b = fx - vx;
+      const double cc = fy * vx - fx * vy;
+      const double ss = c.x * a + c.y * b + cc;
+      fx = c.x; fy = c.y;
+      if (!(ss < 0.0)) {
+        for (int k = trailing + lane; k < idx; k += 32) valid[k] = 1;
+      }
+      trailing = idx;
+      i = idx + 1;
     }
   }
   __syncwarp();
@@ -69,8 +98,8 @@ __global__ void __launch_bounds__(kFvWarps * 32) k_find_valid(SweepDev d)
     bool keep = false;
     int cell = 0;
     if (t < n && valid[t]) {
-      const int gx = world_to_grid(pts[2 * t], ox, d.scale);
-      const int gy = world_to_grid(pts[2 * t + 1], oy, d.scale);
+      const int gx = world_to_grid(P[t].x, ox, d.scale);
+      const int gy = world_to_grid(P[t].y, oy, d.scale);
       keep = is_up_to(gx, d.roi_w) && is_up_to(gy, d.roi_h);
       cell = gx | (gy << 16);
     }
@@ -1046,7 +1075,12 @@ static int sweep_run(b200sm * h)
   cudaStream_t st = h->stream;
   const SweepDev & d = S.dev;
   if (S.nitems > 0) {
-    k_find_valid<<<(S.nitems + kFvWarps - 1) / kFvWarps, kFvWarps * 32, (size_t)kFvWarps * S.max_n, st>>>(d);
+    // warps (= scans) per CTA: as many as fit the shared-memory staging of their points, at most kFvWarps
+    int fvw = (int)std::min<size_t>(kFvWarps, (size_t)200 * 1024 / ((size_t)kFvBytesPerPoint * std::max(S.max_n, 1)));
+    if (fvw < 1) { set_last_error("sweep: scan has too many readings for the shared-memory staging of FindValidPoints"); return B200_ERR_UNSUPPORTED; }
+    const size_t fv_smem = (size_t)fvw * S.max_n * kFvBytesPerPoint;
+    B200_CUDA(cudaFuncSetAttribute(k_find_valid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fv_smem, 48 * 1024)));
+    k_find_valid<<<(S.nitems + fvw - 1) / fvw, fvw * 32, fv_smem, st>>>(d);
     B200_CUDA(cudaGetLastError());
     h->launches++;
   }

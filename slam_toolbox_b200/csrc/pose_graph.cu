@@ -604,12 +604,17 @@ __global__ void __launch_bounds__(512, 1) k_pg_pcg_smem(PgDev d, PcgSmemCfg c, d
 // ------------------------------------------------------------------------------------------
 // k_pg_pcg_2lvl: shared-memory-resident PCG (as k_pg_pcg_smem) with a TWO-LEVEL preconditioner
 //     M^-1 = blockdiag(H_ii + D_i)^-1  +  P Ac^-1 P^T ,   Ac = P^T (H + D) P
-// One aggregate per CTA (its contiguous node range); P holds the aggregate's three rigid-body modes
-// (translation x, y, rotation about the aggregate's centroid) expressed in the Jacobi-scaled
-// variables.  The low-frequency deformation modes that make block-Jacobi CG need thousands of
-// iterations on a pose graph are removed by the coarse solve (measured: ~4.6x fewer iterations).
-//   setup per solve: every CTA builds its 3 rows of Ac, then a block Gauss-Jordan over the grid
-//     (one 3-row pivot exchange per aggregate) leaves each CTA holding ITS 3 rows of Ac^-1 in smem;
+// One aggregate per CTA (its contiguous node range); P holds CM coarse modes per aggregate, expressed
+// in the Jacobi-scaled variables:
+//   CM = 3  the aggregate's rigid-body modes (translation x, y, rotation about its centroid)
+//   CM = 6  the same three modes once more, weighted by s in [-1, 1] = the node's position along the
+//           aggregate (aggregates are stretches of the trajectory): the piecewise-LINEAR deformation
+//           modes.  At cfg4 this costs 1.6x fewer CG iterations than CM = 3 (tools/precond_study.py:
+//           359 vs 568 at LM step 2) for a coarse matrix of 888 instead of 444 rows.
+// The low-frequency deformation modes that make block-Jacobi CG need thousands of iterations on a
+// pose graph are removed by the coarse solve.
+//   setup per solve: every CTA builds its CM rows of Ac, then a block Gauss-Jordan over the grid
+//     (one CM-row pivot exchange per aggregate) leaves each CTA holding ITS CM rows of Ac^-1 in smem;
 //   per CG iteration: 2 flag-based exchanges (no atomic barrier): {p.q, P^T q} and {r.z, r.r};
 //     the coarse residual P^T r is carried by the recurrence rc -= alpha P^T q, identically in
 //     every CTA, so the coarse correction needs no extra exchange.
@@ -617,31 +622,25 @@ __global__ void __launch_bounds__(512, 1) k_pg_pcg_smem(PgDev d, PcgSmemCfg c, d
 // ------------------------------------------------------------------------------------------
 struct Pcg2Cfg {
   int npc, max_slots;     // npc = MAX nodes of one aggregate (array sizing)
-  int ex_doubles;         // size of the exchange scratch (>= 4 G and large enough for the set-up alias)
-  const int32_t * agg_start;   // [G + 1] contiguous node ranges, balanced by block count
+  int ex_doubles;         // size of the exchange scratch (>= (1 + CM) G and large enough for the set-up alias)
+  const int32_t * agg_start;   // [G + 1] contiguous node ranges of equal node count
   const int32_t * agg_of;      // [N] aggregate of every node
   double * gz;            // [N][3]
   double * gp;            // [2][N][3]
-  double * gPt;           // [N][9]   P~ block of every node (rows: node comps, cols: coarse comps)
-  double * gRow;          // [G][3][2 nc] published pivot rows of the block Gauss-Jordan
-  double * grc;           // [G][3]   initial coarse residual
-  double * e1;            // [2][G][4]  {p.q partial, P^T q (3)}
-  double * e2;            // [2][G][2]  {r.z partial, r.r partial}
+  double * gPt;           // [N][10]  P~ base block of every node (rows: node comps, cols: rigid modes) + its s
+  double * gRow;          // [G][CM][2 nc] published pivot rows of the block Gauss-Jordan
+  double * grc;           // [G][CM]  initial coarse residual
+  double * e1;            // [2][G] slots: {p.q partial, P^T q (CM)}
+  double * e2;            // [2][G] slots: {r.z partial, r.r partial}
   unsigned int * gjflag;  // [G]
   unsigned int * bar;     // atomic barrier counter (set-up only)
 };
 
 __device__ __forceinline__ double pg_sentinel() { return __longlong_as_double(0x7FF8DEADBEEF0001LL); }
 __device__ __forceinline__ bool pg_is_sentinel(double v) { return __double_as_longlong(v) == 0x7FF8DEADBEEF0001LL; }
-__device__ __forceinline__ double ld_volatile(const double * p)
-{
-  double v;
-  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // Exchange slots: one 256-byte line per (parity, CTA) so that the all-to-all polling spreads over
-// every L2 slice instead of hammering a few sectors; a slot holds K <= 4 doubles, each self-flagged
+// every L2 slice instead of hammering a few sectors; a slot holds K <= 8 doubles, each self-flagged
 // (a value is "published" when it is not the sentinel).  One thread per source CTA polls with
 // 16-byte loads.
 constexpr int kSlotStride = 32;   // doubles
@@ -652,13 +651,14 @@ __device__ __forceinline__ void ld_volatile2(const double * p, double & a, doubl
 template <int K>
 __device__ __forceinline__ void poll_slots(const double * slots, int G, double * s_out)
 {
+  constexpr int K2 = (K + 1) / 2;
   for (int t = threadIdx.x; t < G; t += blockDim.x) {
     const double * p = slots + (size_t)t * kSlotStride;
-    double v[4];
+    double v[2 * K2];
     bool ok;
     do {
-      ld_volatile2(p, v[0], v[1]);
-      if (K > 2) ld_volatile2(p + 2, v[2], v[3]);
+#pragma unroll
+      for (int k = 0; k < K2; ++k) ld_volatile2(p + 2 * k, v[2 * k], v[2 * k + 1]);
       ok = true;
 #pragma unroll
       for (int k = 0; k < K; ++k) ok = ok && !pg_is_sentinel(v[k]);
@@ -684,19 +684,23 @@ __device__ __forceinline__ double ordered_sum(const double * s, int n, int strid
   return r;
 }
 
+template <int CM>
 __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, double inv_radius, double tol, int max_iter)
 {
+  static_assert(CM == 3 || CM == 6, "coarse modes per aggregate");
+  constexpr int KE1 = 1 + CM;            // doubles of an E1 slot
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  __shared__ double red[4 * 32];
+  __shared__ double red[KE1 * 32];
   __shared__ double bc[1];
-  __shared__ double s_small[16];
+  __shared__ double s_small[CM * CM + 4];
+  __shared__ double s_y[8];
   const int T = blockDim.x, tid = threadIdx.x, G = gridDim.x, I = blockIdx.x;
-  const int nc = 3 * G;
+  const int nc = CM * G;
   const int lo = c.agg_start[I], hi = c.agg_start[I + 1], nloc = hi - lo;
   const int s_lo = d.adj_start[lo], nslots = d.adj_start[hi] - s_lo;
   double * sB = reinterpret_cast<double *>(sm_raw);            // [max_slots][9]
   double * sV = sB + (size_t)c.max_slots * 9;                  // [max_slots][3]
-  double * sEx = sV + (size_t)c.max_slots * 3;                 // [ex_doubles >= 4 G] exchange scratch, right after sV
+  double * sEx = sV + (size_t)c.max_slots * 3;                 // [ex_doubles >= KE1 G] exchange scratch, right after sV
   double * sH = sEx + (size_t)c.ex_doubles;                    // [npc][6]
   double * sMi = sH + (size_t)c.npc * 6;                       // [npc][6]
   double * sR = sMi + (size_t)c.npc * 6;                       // [npc][3] each below
@@ -705,11 +709,12 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
   double * sQ = sP + (size_t)c.npc * 3;
   double * sY = sQ + (size_t)c.npc * 3;
   double * sPt = sY + (size_t)c.npc * 3;                       // [npc][9]
-  double * sAr = sPt + (size_t)c.npc * 9;                      // [3][nc] right half of [Ac | I] -> rows of Ac^-1
-  double * sRc = sAr + (size_t)3 * nc;                         // [nc] coarse residual (identical in all CTAs)
+  double * sS = sPt + (size_t)c.npc * 9;                       // [npc] position of the node along its aggregate, [-1, 1]
+  double * sAr = sS + (size_t)c.npc;                           // [CM][nc] right half of [Ac | I] -> rows of Ac^-1
+  double * sRc = sAr + (size_t)CM * nc;                        // [nc] coarse residual (identical in all CTAs)
   // the left half of [Ac | I] only lives during set-up: it aliases the CG-only scratch sV | sEx
-  // (3 max_slots + ex_doubles >= 3 nc is guaranteed by the host)
-  double * sAl = sV;                                           // [3][nc]
+  // (3 max_slots + ex_doubles >= CM nc is guaranteed by the host)
+  double * sAl = sV;                                           // [CM][nc]
   int * sCol = reinterpret_cast<int *>(sRc + nc);              // [max_slots]
   int * sNode = sCol + c.max_slots;                            // [max_slots] local node of the slot
   int * sStart = sNode + c.max_slots;                          // [npc + 1]
@@ -761,34 +766,49 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
     const double id = 1.0 / (a00 * c00 + a01 * c01 + a02 * c02);
     double * mi = sMi + 6 * n;
     mi[0] = c00 * id; mi[1] = c01 * id; mi[2] = c02 * id; mi[3] = c11 * id; mi[4] = c12 * id; mi[5] = c22 * id;
-    // P~ block: rigid-body modes of the aggregate in Jacobi-scaled variables (y~ = y / s); zero for constant nodes
+    // P~ base block: rigid-body modes of the aggregate in Jacobi-scaled variables (y~ = y / s); zero for constant nodes
     double * pt = sPt + 9 * n;
     const double f = d.is_free[i] ? 1.0 : 0.0;
     const double isx = f / d.scale[3 * i], isy = f / d.scale[3 * i + 1], ist = f / d.scale[3 * i + 2];
     pt[0] = isx; pt[1] = 0;   pt[2] = -(d.x[3 * i + 1] - s_small[1]) * isx;
     pt[3] = 0;   pt[4] = isy; pt[5] = (d.x[3 * i] - s_small[0]) * isy;
     pt[6] = 0;   pt[7] = 0;   pt[8] = ist;
+    const double sn = (CM > 3 && nloc > 1) ? 2.0 * n / (double)(nloc - 1) - 1.0 : 0.0;
+    sS[n] = sn;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) c.gPt[9 * (size_t)i + k] = pt[k];
+    for (int k = 0; k < 9; ++k) c.gPt[10 * (size_t)i + k] = pt[k];
+    c.gPt[10 * (size_t)i + 9] = sn;
   }
   // own exchange slots start empty
-  if (tid < 8) c.e1[((size_t)(tid >> 2) * G + I) * kSlotStride + (tid & 3)] = SENT;
+  if (tid < 2 * KE1) c.e1[((size_t)(tid / KE1) * G + I) * kSlotStride + (tid % KE1)] = SENT;
   if (tid < 4) c.e2[((size_t)(tid >> 1) * G + I) * kSlotStride + (tid & 1)] = SENT;
   bar_target += G;
   grid_barrier(c.bar, bar_target);   // gPt, empty slots visible everywhere
 
-  // ---- coarse operator: this CTA's 3 rows of Ac = P^T (H + D) P, then block Gauss-Jordan ----
-  for (int k = tid; k < 3 * nc; k += T) { sAl[k] = 0.0; sAr[k] = 0.0; }
+  // ---- coarse operator: this CTA's CM rows of Ac = P^T (H + D) P, then block Gauss-Jordan ----
+  // With P_i = [pi | s_i pi], the (I, ct) block of Ac is [[W, Wj], [Wi, Wij]] with W = sum pi^T A_ij pj and the
+  // sums weighted by s_j, s_i, s_i s_j.
+  for (int k = tid; k < CM * nc; k += T) { sAl[k] = 0.0; sAr[k] = 0.0; }
   __syncthreads();
   for (int ct = tid; ct < G; ct += T) {   // a thread owns coarse column block ct; slots are visited in order: deterministic
-    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double acc[CM == 3 ? 9 : 36];
+#pragma unroll
+    for (int k = 0; k < (CM == 3 ? 9 : 36); ++k) acc[k] = 0.0;
+    auto add_block = [&](const double (&w3)[9], double si, double sj) {   // w3 = pi^T A pj
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        acc[k] += w3[k];
+        if constexpr (CM > 3) { acc[9 + k] += sj * w3[k]; acc[18 + k] += si * w3[k]; acc[27 + k] += si * sj * w3[k]; }
+      }
+    };
     for (int s = 0; s < nslots; ++s) {
       const int j = sCol[s];
       if (c.agg_of[j] != ct) continue;
       const double * B = sB + 9 * s, * pi = sPt + 9 * sNode[s];
-      double pj[9], w[9];
+      double pj[9], w[9], w3[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) pj[k] = ld_cg(c.gPt + 9 * (size_t)j + k);
+      for (int k = 0; k < 9; ++k) pj[k] = ld_cg(c.gPt + 10 * (size_t)j + k);
+      const double sj = ld_cg(c.gPt + 10 * (size_t)j + 9);
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -796,12 +816,13 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) acc[3 * r + q] += pi[r] * w[q] + pi[3 + r] * w[3 + q] + pi[6 + r] * w[6 + q];
+        for (int q = 0; q < 3; ++q) w3[3 * r + q] = pi[r] * w[q] + pi[3 + r] * w[3 + q] + pi[6 + r] * w[6 + q];
+      add_block(w3, sS[sNode[s]], sj);
     }
     if (ct == I) {   // diagonal blocks of own nodes
       for (int n = 0; n < nloc; ++n) {
         const double * H = sH + 6 * n, * pi = sPt + 9 * n;
-        double w[9];
+        double w[9], w3[9];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           w[q] = H[0] * pi[q] + H[1] * pi[3 + q] + H[2] * pi[6 + q];
@@ -811,47 +832,80 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int q = 0; q < 3; ++q) acc[3 * r + q] += pi[r] * w[q] + pi[3 + r] * w[3 + q] + pi[6 + r] * w[6 + q];
+          for (int q = 0; q < 3; ++q) w3[3 * r + q] = pi[r] * w[q] + pi[3 + r] * w[3 + q] + pi[6 + r] * w[6 + q];
+        add_block(w3, sS[n], sS[n]);
       }
     }
+    // acc layout: [rb][cb][r][q] with rb / cb = 0 rigid, 1 s-weighted; Ac row = 3 rb + r, column = CM ct + 3 cb + q
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int rb = 0; rb < CM / 3; ++rb)
 #pragma unroll
-      for (int q = 0; q < 3; ++q) sAl[(size_t)r * nc + 3 * ct + q] = acc[3 * r + q];
+      for (int cb = 0; cb < CM / 3; ++cb)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            sAl[(size_t)(3 * rb + r) * nc + CM * ct + 3 * cb + q] = acc[(CM == 3 ? 0 : 18 * rb + 9 * cb) + 3 * r + q];
   }
-  if (tid < 3) sAr[(size_t)tid * nc + 3 * I + tid] = 1.0;   // augmented identity
+  if (tid < CM) sAr[(size_t)tid * nc + CM * I + tid] = 1.0;   // augmented identity
   __syncthreads();
   if (I == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_setup));
   for (int k = 0; k < G; ++k) {
-    double * row = c.gRow + (size_t)k * 6 * nc;   // published pivot rows: [3][nc] left | [3][nc] right
+    double * row = c.gRow + (size_t)k * CM * 2 * nc;   // published pivot rows: [CM][2 nc] (left | right)
     auto elem = [&](int r, int j) -> double & { return j < nc ? sAl[(size_t)r * nc + j] : sAr[(size_t)r * nc + (j - nc)]; };
+    // columns that can be non-zero in pivot rows k: the not yet reduced part of the left half, [CM k, nc), and the part of
+    // the right half filled so far, [0, CM (k + 1)); everything else is 0 and stays 0
+    const int nleft = nc - CM * k, nact = nleft + CM * (k + 1);
     if (I == k) {
-      // pivot block inverse (an aggregate without free nodes has a zero block: treat it as identity)
+      // inverse of the CM x CM pivot block by Gauss-Jordan without pivoting (the block is symmetric positive definite on
+      // its non-degenerate modes); a mode with a zero diagonal (no free node, or the s-modes of a one-node aggregate) has
+      // a zero row and column in all of Ac: it is replaced by the identity
       if (tid == 0) {
-        const double a00 = elem(0, 3 * k), a01 = elem(0, 3 * k + 1), a02 = elem(0, 3 * k + 2);
-        const double a10 = elem(1, 3 * k), a11 = elem(1, 3 * k + 1), a12 = elem(1, 3 * k + 2);
-        const double a20 = elem(2, 3 * k), a21 = elem(2, 3 * k + 1), a22 = elem(2, 3 * k + 2);
-        const double c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
-        const double c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
-        const double c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
-        const double det = a00 * c00 + a01 * c10 + a02 * c20;
-        if (fabs(det) > 1e-300) {
-          const double id = 1.0 / det;
-          s_small[0] = c00 * id; s_small[1] = c01 * id; s_small[2] = c02 * id;
-          s_small[3] = c10 * id; s_small[4] = c11 * id; s_small[5] = c12 * id;
-          s_small[6] = c20 * id; s_small[7] = c21 * id; s_small[8] = c22 * id;
-        } else {
-          for (int q = 0; q < 9; ++q) s_small[q] = (q % 4 == 0) ? 1.0 : 0.0;
+        double a[CM][2 * CM];
+#pragma unroll
+        for (int r = 0; r < CM; ++r)
+#pragma unroll
+          for (int q = 0; q < CM; ++q) { a[r][q] = elem(r, CM * k + q); a[r][CM + q] = (r == q) ? 1.0 : 0.0; }
+#pragma unroll
+        for (int p = 0; p < CM; ++p) {
+          if (!(fabs(a[p][p]) > 1e-300)) {
+#pragma unroll
+            for (int q = 0; q < 2 * CM; ++q) a[p][q] = 0.0;
+#pragma unroll
+            for (int r = 0; r < CM; ++r) a[r][p] = 0.0;
+            a[p][p] = 1.0; a[p][CM + p] = 1.0;
+          }
+          const double ip = 1.0 / a[p][p];
+#pragma unroll
+          for (int q = 0; q < 2 * CM; ++q) a[p][q] *= ip;
+#pragma unroll
+          for (int r = 0; r < CM; ++r) {
+            if (r == p) continue;
+            const double m = a[r][p];
+#pragma unroll
+            for (int q = 0; q < 2 * CM; ++q) a[r][q] -= m * a[p][q];
+          }
         }
+#pragma unroll
+        for (int r = 0; r < CM; ++r)
+#pragma unroll
+          for (int q = 0; q < CM; ++q) s_small[CM * r + q] = a[r][CM + q];
       }
       __syncthreads();
-      for (int j = tid; j < 2 * nc; j += T) {
-        const double v0 = elem(0, j), v1 = elem(1, j), v2 = elem(2, j);
-        const double n0 = s_small[0] * v0 + s_small[1] * v1 + s_small[2] * v2;
-        const double n1 = s_small[3] * v0 + s_small[4] * v1 + s_small[5] * v2;
-        const double n2 = s_small[6] * v0 + s_small[7] * v1 + s_small[8] * v2;
-        elem(0, j) = n0; elem(1, j) = n1; elem(2, j) = n2;
-        row[j] = n0; row[2 * nc + j] = n1; row[4 * nc + j] = n2;
+      for (int t = tid; t < nact; t += T) {
+        const int j = t < nleft ? CM * k + t : nc + (t - nleft);
+        double v[CM], o[CM];
+#pragma unroll
+        for (int r = 0; r < CM; ++r) v[r] = elem(r, j);
+#pragma unroll
+        for (int r = 0; r < CM; ++r) {
+          double a = 0;
+#pragma unroll
+          for (int q = 0; q < CM; ++q) a += s_small[CM * r + q] * v[q];
+          o[r] = a;
+        }
+#pragma unroll
+        for (int r = 0; r < CM; ++r) { elem(r, j) = o[r]; row[(size_t)r * 2 * nc + j] = o[r]; }
       }
       __syncthreads();
       if (tid == 0) {
@@ -864,14 +918,21 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(c.gjflag + k) : "memory");
         } while (v == 0u);
-        for (int q = 0; q < 9; ++q) s_small[q] = elem(q / 3, 3 * k + (q % 3));   // my multipliers
       }
+      if (tid < CM * CM) s_small[tid] = elem(tid / CM, CM * k + (tid % CM));   // my multipliers (read before they are eliminated)
       __syncthreads();
-      for (int j = tid; j < 2 * nc; j += T) {
-        const double r0 = ld_cg(row + j), r1 = ld_cg(row + 2 * nc + j), r2 = ld_cg(row + 4 * nc + j);
-        elem(0, j) -= s_small[0] * r0 + s_small[1] * r1 + s_small[2] * r2;
-        elem(1, j) -= s_small[3] * r0 + s_small[4] * r1 + s_small[5] * r2;
-        elem(2, j) -= s_small[6] * r0 + s_small[7] * r1 + s_small[8] * r2;
+      for (int t = tid; t < nact; t += T) {
+        const int j = t < nleft ? CM * k + t : nc + (t - nleft);
+        double pr[CM];
+#pragma unroll
+        for (int q = 0; q < CM; ++q) pr[q] = ld_cg(row + (size_t)q * 2 * nc + j);
+#pragma unroll
+        for (int r = 0; r < CM; ++r) {
+          double a = 0;
+#pragma unroll
+          for (int q = 0; q < CM; ++q) a += s_small[CM * r + q] * pr[q];
+          elem(r, j) -= a;
+        }
       }
       __syncthreads();
     }
@@ -879,7 +940,6 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
   if (I == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_gj));
   // rows of Ac^-1 are now sAr[r * nc + j]
   __syncthreads();
-  const double * Ai0 = sAr, * Ai1 = sAr + nc, * Ai2 = sAr + 2 * nc;
 
   // ---- CG start: r = b, coarse residual, z = M^-1 r ----
   double accb[1] = {0};
@@ -890,10 +950,14 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
     accb[0] += b * b;
   }
   __syncthreads();
-  if (tid < 3) {
+  if (tid < CM) {   // P^T r of this aggregate, fixed order
+    const int cb = tid / 3, q = tid % 3;
     double a = 0;
-    for (int n = 0; n < nloc; ++n) a += sPt[9 * n + tid] * sR[3 * n] + sPt[9 * n + 3 + tid] * sR[3 * n + 1] + sPt[9 * n + 6 + tid] * sR[3 * n + 2];
-    c.grc[3 * I + tid] = a;
+    for (int n = 0; n < nloc; ++n) {
+      const double v = sPt[9 * n + q] * sR[3 * n] + sPt[9 * n + 3 + q] * sR[3 * n + 1] + sPt[9 * n + 6 + q] * sR[3 * n + 2];
+      a += cb ? sS[n] * v : v;
+    }
+    c.grc[CM * I + tid] = a;
   }
   block_sum<1>(accb, red);
   if (tid == 0) d.partial[I] = accb[0];
@@ -905,16 +969,15 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
 
   // z = blockJacobi^-1 r + P Ac^-1 rc ; returns partial r.z and r.r through a2
   auto apply_precond = [&](double (&a2)[2]) {
-    if (tid < 96) {   // 3 warps: one row of Ac^-1 each
+    if (tid < 32 * CM) {   // CM warps: one row of Ac^-1 each
       const int w = tid >> 5, l = tid & 31;
-      const double * Ai = w == 0 ? Ai0 : (w == 1 ? Ai1 : Ai2);
+      const double * Ai = sAr + (size_t)w * nc;
       double a = 0;
       for (int j = l; j < nc; j += 32) a += Ai[j] * sRc[j];
       a = warp_sum(a);
-      if (l == 0) s_small[12 + w] = a;
+      if (l == 0) s_y[w] = a;
     }
     __syncthreads();
-    const double y0 = s_small[12], y1 = s_small[13], y2 = s_small[14];
     a2[0] = 0; a2[1] = 0;
     for (int k = tid; k < 3 * nloc; k += T) {
       const int n = k / 3, r = k - 3 * n;
@@ -924,6 +987,8 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
       if (r == 0) z = mi[0] * r0 + mi[1] * r1 + mi[2] * r2;
       else if (r == 1) z = mi[1] * r0 + mi[3] * r1 + mi[4] * r2;
       else z = mi[2] * r0 + mi[4] * r1 + mi[5] * r2;
+      double y0 = s_y[0], y1 = s_y[1], y2 = s_y[2];
+      if constexpr (CM > 3) { const double sn = sS[n]; y0 += sn * s_y[3]; y1 += sn * s_y[4]; y2 += sn * s_y[5]; }
       z += pt[0] * y0 + pt[1] * y1 + pt[2] * y2;
       sZ[k] = z;
       c.gz[3 * lo + k] = z;
@@ -970,7 +1035,9 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
       __syncthreads();
       for (int k = tid; k < 3 * nloc; k += T) { sP[k] = sQ[k]; gpn[3 * lo + k] = sQ[k]; }
       __syncthreads();
-      double a1[4] = {0, 0, 0, 0};   // p.q and the three components of P^T q of this aggregate
+      double a1[KE1];   // p.q and the CM components of P^T q of this aggregate
+#pragma unroll
+      for (int k = 0; k < KE1; ++k) a1[k] = 0.0;
       for (int k = tid; k < 3 * nloc; k += T) {
         const int n = k / 3, r = k - 3 * n;
         const double * H = sH + 6 * n;
@@ -986,24 +1053,27 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
         sQ[k] = q;
         const double * pt = sPt + 9 * n + 3 * r;
         a1[0] += sP[k] * q;
-        a1[1] += pt[0] * q; a1[2] += pt[1] * q; a1[3] += pt[2] * q;
+        const double u0 = pt[0] * q, u1 = pt[1] * q, u2 = pt[2] * q;
+        a1[1] += u0; a1[2] += u1; a1[3] += u2;
+        if constexpr (CM > 3) { const double sn = sS[n]; a1[4] += sn * u0; a1[5] += sn * u1; a1[6] += sn * u2; }
       }
-      block_sum<4>(a1, red);
+      block_sum<KE1>(a1, red);
       PG_TICK(tB);
       if (tid == 0) {
         __threadfence();   // p_new of this CTA visible before the flagged values
         double * m = e1 + (size_t)I * kSlotStride;
-        m[1] = a1[1]; m[2] = a1[2]; m[3] = a1[3];
+#pragma unroll
+        for (int k = 1; k < KE1; ++k) m[k] = a1[k];
         m[0] = a1[0];
       }
-      poll_slots<4>(e1, G, sEx);
+      poll_slots<KE1>(e1, G, sEx);
       PG_TICK(tC);
       // every CTA published E1(it) only after it finished reading E2(it-1): those slots can be recycled now
       if (it > 0 && tid < 2) c.e2[((size_t)(par ^ 1) * G + I) * kSlotStride + tid] = SENT;
-      const double pq = ordered_sum(sEx, G, 4, 0, bc);
+      const double pq = ordered_sum(sEx, G, KE1, 0, bc);
       const double alpha = rz / pq;
       // ---- phase B ----
-      for (int k = tid; k < nc; k += T) sRc[k] -= alpha * sEx[4 * (k / 3) + 1 + (k % 3)];
+      for (int k = tid; k < nc; k += T) sRc[k] -= alpha * sEx[KE1 * (k / CM) + 1 + (k % CM)];
       for (int k = tid; k < 3 * nloc; k += T) { sY[k] += alpha * sP[k]; sR[k] -= alpha * sQ[k]; }
       __syncthreads();
       apply_precond(a2);
@@ -1018,16 +1088,16 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
       poll_slots<2>(e2, G, sEx);
       PG_TICK(tE);
       // every CTA published E2(it) only after it finished reading E1(it): recycle own E1(it) slots
-      if (tid < 4) c.e1[((size_t)par * G + I) * kSlotStride + tid] = SENT;
+      if (tid < KE1) c.e1[((size_t)par * G + I) * kSlotStride + tid] = SENT;
       if (tid < 32) {
         double u = 0, w = 0;
         for (int i = tid; i < G; i += 32) { u += sEx[2 * i]; w += sEx[2 * i + 1]; }
         u = warp_sum(u); w = warp_sum(w);
-        if (tid == 0) { s_small[10] = u; s_small[11] = w; }
+        if (tid == 0) { s_small[0] = u; s_small[1] = w; }
       }
       __syncthreads();
-      const double rz_new = s_small[10];
-      rr = s_small[11];
+      const double rz_new = s_small[0];
+      rr = s_small[1];
       ++it;
       cur ^= 1;
       if (!(rr > stop) || !(pq > 0.0)) break;
@@ -1047,6 +1117,7 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
     d.scalars[13] = (double)tA; d.scalars[14] = (double)tB; d.scalars[15] = (double)tC;
     d.scalars[6] = (double)tD; d.scalars[7] = (double)tE;
   }
+#undef PG_TICK
 }
 
 // candidate point: delta = -(y * scale) ; xc = x (+) delta on free nodes; partial ||x - xc||^2
@@ -1128,6 +1199,7 @@ struct b200pg {
   DevBuf<double> d_gz, d_gp, d_gPt, d_gRow, d_grc, d_e1, d_e2;
   bool debug = false;
   int precond = 1;   // 1 = two-level (rigid-mode aggregation) + block Jacobi, 0 = block Jacobi only
+  int coarse_modes = 6;   // two-level: coarse modes per aggregate (6 = rigid + linear deformation, 3 = rigid only)
   DevBuf<unsigned int> d_bar;
   bool force_global_pcg = false;
   DevBuf<double> d_z, d_U, d_x, d_xc, d_scale, d_lin, d_Hd, d_g, d_diag, d_y, d_pr, d_pz, d_pp0, d_pp1, d_pq, d_Minv,
@@ -1211,6 +1283,7 @@ struct Lm {
   bool use_2lvl = false;
   int blocks2 = 0;
   size_t smem2_bytes = 0;
+  int cm2 = 3;
   Pcg2Cfg cfg2{};
   cudaStream_t st;
 
@@ -1366,20 +1439,30 @@ static int solve(b200pg * h, b200pg_summary * sum)
         max_slots = std::max(max_slots, adj_start[agg_start[c + 1]] - adj_start[agg_start[c]]);
         npc = std::max(npc, agg_start[c + 1] - agg_start[c]);
       }
-      const int nc = 3 * Gu;
-      const int ex_doubles = std::max(4 * Gu, 3 * nc - 3 * max_slots);
-      const size_t bytes2 = ((size_t)max_slots * 12 + (size_t)npc * 36 + (size_t)4 * nc + (size_t)ex_doubles) * sizeof(double) +
-                            ((size_t)2 * max_slots + npc + 1) * sizeof(int) + 16;
-      if (bytes2 > 220 * 1024) continue;
-      int occ = 0;
-      B200_CUDA(cudaFuncSetAttribute(k_pg_pcg_2lvl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2));
-      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pg_pcg_2lvl, 256, bytes2));
-      if (h->debug) fprintf(stderr, "[b200pg] two-level plan: %d aggregates, <= %d nodes and <= %d blocks each, %zu B smem, occupancy %d/SM\n", Gu, npc, max_slots, bytes2, occ);
-      if (occ * sms < Gu) continue;
-      L.use_2lvl = true; L.smem2_bytes = bytes2; L.blocks2 = Gu;
+      // coarse modes per aggregate: 6 (rigid + piecewise-linear deformation) when it fits shared memory, else 3
+      int cm = 0, nc = 0, ex_doubles = 0;
+      size_t bytes2 = 0;
+      for (int try_cm : {6, 3}) {
+        if (try_cm > h->coarse_modes) continue;
+        nc = try_cm * Gu;
+        ex_doubles = std::max((1 + try_cm) * Gu, try_cm * nc - 3 * max_slots);
+        bytes2 = ((size_t)max_slots * 12 + (size_t)npc * 37 + (size_t)(try_cm + 1) * nc + (size_t)ex_doubles) * sizeof(double) +
+                 ((size_t)2 * max_slots + npc + 1) * sizeof(int) + 16;
+        if (bytes2 > 220 * 1024) continue;
+        int occ = 0;
+        const void * fn = try_cm == 6 ? (const void *)k_pg_pcg_2lvl<6> : (const void *)k_pg_pcg_2lvl<3>;
+        B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes2));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 256, bytes2));
+        if (h->debug) fprintf(stderr, "[b200pg] two-level plan: %d aggregates x %d modes, <= %d nodes and <= %d blocks each, %zu B smem, occupancy %d/SM\n", Gu, try_cm, npc, max_slots, bytes2, occ);
+        if (occ * sms < Gu) continue;
+        cm = try_cm;
+        break;
+      }
+      if (!cm) continue;
+      L.use_2lvl = true; L.smem2_bytes = bytes2; L.blocks2 = Gu; L.cm2 = cm;
       h->d_gz.reserve(n3); h->d_gp.reserve(2 * n3);
       h->d_bar.reserve(std::max<size_t>(4096, (size_t)Gu + 4));
-      h->d_gPt.reserve(9 * (size_t)N); h->d_gRow.reserve((size_t)Gu * 6 * nc); h->d_grc.reserve(nc);
+      h->d_gPt.reserve(10 * (size_t)N); h->d_gRow.reserve((size_t)Gu * cm * 2 * nc); h->d_grc.reserve(nc);
       h->d_e1.reserve((size_t)2 * Gu * kSlotStride); h->d_e2.reserve((size_t)2 * Gu * kSlotStride);
       up(h->d_agg_start, agg_start, st); up(h->d_agg_of, agg_of, st);
       B200_CUDA(cudaStreamSynchronize(st));   // the two vectors go out of scope
@@ -1427,7 +1510,7 @@ static int solve(b200pg * h, b200pg_summary * sum)
       if (L.use_2lvl) {
         B200_CUDA(cudaMemsetAsync(h->d_bar.p, 0, (size_t)(L.blocks2 + 1) * sizeof(unsigned int), st));
         void * args[] = {&d, &L.cfg2, &inv_radius, &tol, &max_iter};
-        B200_CUDA(cudaLaunchCooperativeKernel((void *)k_pg_pcg_2lvl, dim3(L.blocks2), dim3(256), args, L.smem2_bytes, st));
+        B200_CUDA(cudaLaunchCooperativeKernel(L.cm2 == 6 ? (void *)k_pg_pcg_2lvl<6> : (void *)k_pg_pcg_2lvl<3>, dim3(L.blocks2), dim3(256), args, L.smem2_bytes, st));
       } else if (L.use_smem) {
         B200_CUDA(cudaMemsetAsync(h->d_bar.p, 0, sizeof(unsigned int), st));
         void * args[] = {&d, &L.cfg, &inv_radius, &tol, &max_iter};
@@ -1548,6 +1631,7 @@ int b200pg_create(const b200pg_opts * opts, b200pg ** out)
   if (const char * e = getenv("B200PG_FORCE_GLOBAL_PCG")) h->force_global_pcg = atoi(e) != 0;
   if (const char * e = getenv("B200PG_DEBUG")) h->debug = atoi(e) != 0;
   if (const char * e = getenv("B200PG_PRECOND")) h->precond = std::string(e) == "jacobi" ? 0 : 1;
+  if (const char * e = getenv("B200PG_COARSE_MODES")) h->coarse_modes = atoi(e) >= 6 ? 6 : 3;
   *out = h.release();
   return B200_OK;
   B200_GUARD_END

@@ -138,6 +138,21 @@ def test_two_level_and_jacobi_preconditioners_agree(monkeypatch):
     assert s1.summary.pcg_iterations < 0.6 * s2.summary.pcg_iterations, (s1.summary.pcg_iterations, s2.summary.pcg_iterations)
 
 
+def test_linear_coarse_modes_against_rigid_only(monkeypatch):
+    """6 coarse modes per aggregate (rigid + piecewise-linear deformation, the default) against the rigid-only coarse space:
+    same LM trajectory, same poses to PCG accuracy, fewer CG iterations."""
+    g = synth.make_pose_graph(13, 6000, 22000, sigma_xy=0.03, sigma_th=0.01)
+    s1 = build(g)
+    assert s1.Compute()
+    monkeypatch.setenv("B200PG_COARSE_MODES", "3")
+    s2 = build(g)
+    assert s2.Compute()
+    assert s1.summary.iterations == s2.summary.iterations and s1.summary.successful_steps == s2.summary.successful_steps
+    dxy, dth = diff(s1.GetCorrections()[1], s2.GetCorrections()[1])
+    assert dxy < 1e-7 and dth < 1e-8, (dxy, dth)
+    assert s1.summary.pcg_iterations < 0.85 * s2.summary.pcg_iterations, (s1.summary.pcg_iterations, s2.summary.pcg_iterations)
+
+
 @pytest.mark.parametrize("loss,code", [("huber", 1), ("cauchy", 2)])
 def test_robust_losses_match_oracle_and_reject_outliers(loss, code):
     """ceres_loss_function = HuberLoss / CauchyLoss (scale 0.7, solvers/ceres_solver.cpp:82-94) with gross outliers

@@ -752,6 +752,7 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
     for (int n = 0; n < nloc; ++n)
       if (d.is_free[lo + n]) { cx += d.x[3 * (lo + n)]; cy += d.x[3 * (lo + n) + 1]; ++cnt; }
     s_small[0] = cnt ? cx / cnt : 0.0; s_small[1] = cnt ? cy / cnt : 0.0;
+    s_small[2] = (double)cnt;
   }
   __syncthreads();
   for (int n = tid; n < nloc; n += T) {
@@ -773,7 +774,9 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
     pt[0] = isx; pt[1] = 0;   pt[2] = -(d.x[3 * i + 1] - s_small[1]) * isx;
     pt[3] = 0;   pt[4] = isy; pt[5] = (d.x[3 * i] - s_small[0]) * isy;
     pt[6] = 0;   pt[7] = 0;   pt[8] = ist;
-    const double sn = (CM > 3 && nloc > 1) ? 2.0 * n / (double)(nloc - 1) - 1.0 : 0.0;
+    // the s-weighted modes need two free nodes to be independent of the rigid ones; otherwise they are switched off
+    // (s = 0 gives zero rows and columns of Ac, which the Gauss-Jordan replaces by the identity)
+    const double sn = (CM > 3 && nloc > 1 && s_small[2] >= 2.0) ? 2.0 * n / (double)(nloc - 1) - 1.0 : 0.0;
     sS[n] = sn;
 #pragma unroll
     for (int k = 0; k < 9; ++k) c.gPt[10 * (size_t)i + k] = pt[k];
@@ -866,9 +869,12 @@ __global__ void __launch_bounds__(256, 2) k_pg_pcg_2lvl(PgDev d, Pcg2Cfg c, doub
         for (int r = 0; r < CM; ++r)
 #pragma unroll
           for (int q = 0; q < CM; ++q) { a[r][q] = elem(r, CM * k + q); a[r][CM + q] = (r == q) ? 1.0 : 0.0; }
+        double d0[CM];
+#pragma unroll
+        for (int p = 0; p < CM; ++p) d0[p] = fabs(a[p][p]);
 #pragma unroll
         for (int p = 0; p < CM; ++p) {
-          if (!(fabs(a[p][p]) > 1e-300)) {
+          if (!(fabs(a[p][p]) > 1e-12 * d0[p]) || !(d0[p] > 1e-300)) {   // zero or (numerically) dependent mode
 #pragma unroll
             for (int q = 0; q < 2 * CM; ++q) a[p][q] = 0.0;
 #pragma unroll

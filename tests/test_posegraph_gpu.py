@@ -138,6 +138,40 @@ def test_two_level_and_jacobi_preconditioners_agree(monkeypatch):
     assert s1.summary.pcg_iterations < 0.6 * s2.summary.pcg_iterations, (s1.summary.pcg_iterations, s2.summary.pcg_iterations)
 
 
+def test_tiny_and_degenerate_graphs_match_oracle():
+    """Aggregates the coarse space must survive: a single free node (the linear modes would repeat the rigid ones), three
+    nodes, and isolated (never optimised) nodes sharing an aggregate with free ones."""
+    cov = np.diag([0.01, 0.01, 0.001])
+    for n, edges in ((2, [(0, 1)]), (3, [(0, 1), (1, 2), (0, 2)])):
+        poses = np.array([[0, 0, 0], [1.05, 0.1, 0.05], [2.1, -0.05, -0.02]])[:n]
+        ea, eb = np.array([a for a, _ in edges]), np.array([b for _, b in edges])
+        z = np.array([[float(b - a), 0.0, 0.0] for a, b in edges])
+        xo, so = PG.solve(poses, ea, eb, z, cov=np.repeat(cov[None], len(edges), axis=0))
+        s = api.ScanSolver()
+        for i in range(n):
+            s.AddNode(i, poses[i])
+        for (a, b), zz in zip(edges, z):
+            assert s.AddConstraint(a, b, zz, cov)
+        assert s.Compute()
+        dxy, dth = diff(s.GetCorrections()[1], xo)
+        assert dxy < TOL_XY and dth < TOL_TH, (n, dxy, dth)
+    g = synth.make_pose_graph(21, 40, 70, sigma_xy=0.03, sigma_th=0.01, min_gap=3)
+    xo, so = PG.solve(g["init"], g["edge_a"], g["edge_b"], g["z"], cov=g["cov"])
+    s = api.ScanSolver()
+    for k, (nid, p) in enumerate(zip(g["ids"], g["init"])):
+        s.AddNode(int(nid), p)
+        if k % 3 == 0:
+            s.AddNode(10000 + k, np.array([5.0, 5.0, 0.3]))       # isolated: stays where it is
+    for a, b, zz, c in zip(g["edge_a"], g["edge_b"], g["z"], g["cov"]):
+        assert s.AddConstraint(int(a), int(b), zz, c)
+    assert s.Compute() and s.summary.iterations == so.iterations
+    ids, x = s.GetCorrections()
+    keep = ids < 10000
+    dxy, dth = diff(x[keep], xo)
+    assert dxy < TOL_XY and dth < TOL_TH, (dxy, dth)
+    assert np.array_equal(x[~keep], np.tile([5.0, 5.0, 0.3], ((~keep).sum(), 1)))
+
+
 def test_linear_coarse_modes_against_rigid_only(monkeypatch):
     """6 coarse modes per aggregate (rigid + piecewise-linear deformation, the default) against the rigid-only coarse space:
     same LM trajectory, same poses to PCG accuracy, fewer CG iterations."""

@@ -448,7 +448,6 @@ __global__ void __launch_bounds__(kFastThreads, 1) k_sweep_fast(SweepDev d, Fast
 
   for (int pair = blockIdx.x; pair < d.npairs; pair += gridDim.x) {
     const int q = d.pair_query[pair];
-    const int X0 = f.origin[2 * q], Y0 = f.origin[2 * q + 1];
     for (int i = threadIdx.x; i < nA * P; i += blockDim.x) A[i] = 0;
     const int it0 = d.pair_item_start[pair], it1 = d.pair_item_start[pair + 1];
 
@@ -941,7 +940,7 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   const size_t smem = (size_t)sub_rows * kSubPitchW * 4 + (size_t)nA * nX * nY * 4;
   if (smem > 227 * 1024 - 1024) return bail(4);
   if ((size_t)5 * nX * nY * sizeof(double) > (size_t)sub_rows * kSubPitchW * 4) return bail(5);   // epilogue scratch reuses S
-  std::vector<int32_t> origin(2 * (size_t)nq), cls_start((size_t)nq * nA * 33), slow, slow_start((size_t)nq * (nA + 1));
+  std::vector<int32_t> cls_start((size_t)nq * nA * 33), slow, slow_start((size_t)nq * (nA + 1));
   std::vector<uint16_t> beams, mult;
   std::vector<int32_t> wrap2, wrap2_start((size_t)nq * nA * 4 + 1);
   std::vector<int32_t> edge, edge_start((size_t)nq * nA * 17);
@@ -953,7 +952,6 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
     for (int k = 1; k < nX; ++k) if (pl.xs[k] != pl.xs[0] + 2 * k) return bail(6);   // coarse step must be exactly 2 cells
     for (int k = 1; k < nY; ++k) if (pl.ys[k] != pl.ys[0] + 2 * k) return bail(7);
     const int X0 = pl.xs[0], Y0 = pl.ys[0];
-    origin[2 * q] = X0; origin[2 * q + 1] = Y0;
     std::vector<uint16_t> group[16];
     std::vector<int32_t> wgroup[4], egroup[16];
     for (int a = 0; a < nA; ++a) {
@@ -1027,7 +1025,6 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   }
   wrap2_start[(size_t)nq * nA * 4] = (int32_t)wrap2.size();
   // slow_start must be relative to one array: it is (single vector `slow`)
-  h2d(S.d_fast_origin, origin.data(), origin.size(), st);
   h2d(S.d_fast_cls, cls_start.data(), cls_start.size(), st);
   S.d_fast_beams.reserve(std::max<size_t>(beams.size(), 1) + 8);
   if (!beams.empty()) B200_CUDA(cudaMemcpyAsync(S.d_fast_beams.p, beams.data(), beams.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
@@ -1048,7 +1045,6 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   S.fast_info[0] = 1; S.fast_info[1] = (int32_t)beams.size(); S.fast_info[2] = n_edge; S.fast_info[3] = (int32_t)slow.size() - 1; S.fast_info[4] = 0;
   S.fast.sub_rows = sub_rows;
   S.fast.xtiles = xtiles;
-  S.fast.origin = S.d_fast_origin.p;
   S.fast.beams = S.d_fast_beams.p;
   S.fast.mult = S.d_fast_mult.p;
   S.fast.cls_start = S.d_fast_cls.p;

@@ -128,7 +128,6 @@ struct FastDev {
   int enabled;
   int sub_rows;                  // allocated sub-grid rows (incl. padding rows)
   int xtiles;                    // ceil((nX + 3) / 16)
-  const int32_t * origin;        // [nq][2]  grid column / row of pose (0, 0)
   const uint16_t * beams;        // FAST descriptors, grouped; per group: plain entries, then multi entries
   const uint16_t * mult;         // multiplicity of every entry (1 for plain entries)
   const int32_t * cls_start;     // [nq][nA][33]: group g = phase * 4 + m -> [2g] plain begin, [2g+1] multi begin, [2g+2] end
@@ -162,7 +161,7 @@ struct SweepHost {
   DevBuf<double> d_qgeom, d_center, d_qd, d_angpen, d_points, d_ws_probs;
   DevBuf<uint8_t> d_ws_grid, d_kernel;
   DevBuf<uint16_t> d_fast_beams, d_fast_mult;
-  DevBuf<int32_t> d_fast_origin, d_fast_cls, d_fast_slow, d_fast_slow_start, d_fast_wrap2, d_fast_wrap2_start, d_fast_edge, d_fast_edge_start;
+  DevBuf<int32_t> d_fast_cls, d_fast_slow, d_fast_slow_start, d_fast_wrap2, d_fast_wrap2_start, d_fast_edge, d_fast_edge_start;
   FastDev fast{};
   size_t fast_smem = 0;
   int32_t fast_info[5] = {0, 0, 0, 0, 0};   // enabled, FAST descriptors, CLIP beams, WRAP beams, reason the fast path was refused

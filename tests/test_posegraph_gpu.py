@@ -138,6 +138,18 @@ def test_two_level_and_jacobi_preconditioners_agree(monkeypatch):
     assert s1.summary.pcg_iterations < 0.6 * s2.summary.pcg_iterations, (s1.summary.pcg_iterations, s2.summary.pcg_iterations)
 
 
+def test_realistic_sparse_graph_shape():
+    """The reference's own recorded mapping run has 4,265 vertices and ~5,210 edges (test/constraints_on_graph.dat):
+    a long chain with few loop closures, far sparser than cfg4."""
+    g = synth.make_pose_graph(5, 4265, 5210, sigma_xy=0.03, sigma_th=0.01)
+    xo, so = PG.solve(g["init"], g["edge_a"], g["edge_b"], g["z"], cov=g["cov"])
+    s = build(g)
+    assert s.Compute()
+    assert s.summary.iterations == so.iterations and abs(s.summary.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    dxy, dth = diff(s.GetCorrections()[1], xo)
+    assert dxy < TOL_XY and dth < TOL_TH, (dxy, dth)
+
+
 def test_tiny_and_degenerate_graphs_match_oracle():
     """Aggregates the coarse space must survive: a single free node (the linear modes would repeat the rigid ones), three
     nodes, and isolated (never optimised) nodes sharing an aggregate with free ones."""

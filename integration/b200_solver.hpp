@@ -36,7 +36,7 @@ public:
   }
   const karto::ScanSolver::IdPoseVector & GetCorrections() const override { return corrections_; }
   void Clear() override { corrections_.clear(); b200pg_clear(h_); }
-  void Reset() override { corrections_.clear(); b200pg_reset(h_); }
+  void Reset() override { corrections_.clear(); ids_.clear(); b200pg_reset(h_); }
 
   void AddNode(karto::Vertex<karto::LocalizedRangeScan> * v) override   // ceres_solver.cpp:317-336
   {
@@ -44,7 +44,7 @@ public:
     if (getenv("B200_TRACE")) fprintf(stderr, "AddNode %p\n", (void*)v);
     const karto::Pose2 p = v->GetObject()->GetCorrectedPose();
     const double pose[3] = {p.GetX(), p.GetY(), p.GetHeading()};
-    b200pg_add_node(h_, v->GetObject()->GetUniqueId(), pose);
+    if (b200pg_add_node(h_, v->GetObject()->GetUniqueId(), pose) == B200_OK) ids_.push_back(v->GetObject()->GetUniqueId());
   }
   void AddConstraint(karto::Edge<karto::LocalizedRangeScan> * e) override   // ceres_solver.cpp:339-392
   {
@@ -58,7 +58,12 @@ public:
     for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) cov[3 * r + k] = c(r, k);
     b200pg_add_edge(h_, e->GetSource()->GetObject()->GetUniqueId(), e->GetTarget()->GetObject()->GetUniqueId(), z, cov);
   }
-  void RemoveNode(kt_int32s id) override { b200pg_remove_node(h_, id); }
+  void RemoveNode(kt_int32s id) override
+  {
+    if (b200pg_remove_node(h_, id) != B200_OK) return;
+    for (size_t i = 0; i < ids_.size(); ++i)
+      if (ids_[i] == id) { ids_.erase(ids_.begin() + i); break; }
+  }
   void RemoveConstraint(kt_int32s a, kt_int32s b) override { b200pg_remove_edge(h_, a, b); }
   void ModifyNode(const int & id, Eigen::Vector3d pose) override
   {
@@ -71,12 +76,29 @@ public:
     if (b200pg_get_node(h_, id, p) == B200_OK) yaw = p[2];
   }
 
+  // the raw node store for visualisation (ceres_solver.cpp:474-479, used by src/loop_closure_assistant.cpp:161):
+  // a host copy of the nodes as the library holds them now, refreshed on every call
+  std::unordered_map<int, Eigen::Vector3d> * getGraph() override
+  {
+    graph_.clear();
+    for (int id : ids_) {
+      double p[3];
+      if (b200pg_get_node(h_, id, p) != B200_OK) continue;
+      Eigen::Vector3d v;
+      v(0) = p[0]; v(1) = p[1]; v(2) = p[2];
+      graph_[id] = v;
+    }
+    return &graph_;
+  }
+
   int computes() const { return computes_; }
   double solve_ms() const { return solve_ms_; }
 
 private:
   b200pg * h_ = nullptr;
   karto::ScanSolver::IdPoseVector corrections_;
+  std::vector<int> ids_;                                  // node ids in insertion order
+  std::unordered_map<int, Eigen::Vector3d> graph_;
   int computes_ = 0;
   double solve_ms_ = 0.0;
 };

@@ -74,8 +74,13 @@ def run_inprocess(which: str, ranges: np.ndarray, odom: np.ndarray, params: dict
     if which == "b200":
         L.b200_shim_match_calls.restype = C.c_long
         matches = int(L.b200_shim_match_calls())
-    out = dict(poses=poses, kept=np.array(kept), process_seconds=st[0], solver_computes=int(st[1]), solver_ms=st[2],
-               edges=int(st[3]), scans=int(st[4]), match_calls=matches)
+    L.krep_solver_graph.argtypes = [C.c_void_p, C.POINTER(C.c_int), _DP, C.c_int]
+    gids = np.zeros(max(n, 1), dtype=np.int32)
+    gposes = np.zeros((max(n, 1), 3))
+    gn = L.krep_solver_graph(h, gids.ctypes.data_as(C.POINTER(C.c_int)), gposes.ctypes.data_as(_DP), n) if use_solver else 0
+    order = np.argsort(gids[:min(gn, n)])
+    out = dict(graph_nodes=gn, graph_ids=gids[:min(gn, n)][order], graph_poses=gposes[:min(gn, n)][order], poses=poses, kept=np.array(kept),
+               process_seconds=st[0], solver_computes=int(st[1]), solver_ms=st[2], edges=int(st[3]), scans=int(st[4]), match_calls=matches)
     if map_resolution:
         # the map-publish step over all processed scans: reference CPU build and the b200og binding, same process
         L.krep_occupancy.restype = C.c_double

@@ -130,6 +130,20 @@ void krep_poses(void * rp, double * out)
   }
 }
 
+// ScanSolver::getGraph() of the adapter: number of nodes; ids / poses filled up to cap
+int krep_solver_graph(void * rp, int * ids, double * poses, int cap)
+{
+  Replay * r = static_cast<Replay *>(rp);
+  if (!r->solver) return 0;
+  std::unordered_map<int, Eigen::Vector3d> * g = r->solver->getGraph();
+  int k = 0;
+  for (const auto & kv : *g) {
+    if (k < cap) { ids[k] = kv.first; poses[3 * k] = kv.second(0); poses[3 * k + 1] = kv.second(1); poses[3 * k + 2] = kv.second(2); }
+    ++k;
+  }
+  return k;
+}
+
 // stats: process seconds, solver computes, solver device ms, graph edges, graph vertices
 void krep_stats(void * rp, double out[5])
 {

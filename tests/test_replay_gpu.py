@@ -25,6 +25,8 @@ def test_mapper_process_replay_is_identical_with_the_gpu_matcher():
     assert a["edges"] == b["edges"] and a["solver_computes"] == b["solver_computes"]
     assert np.array_equal(a["poses"], b["poses"])
     assert b["match_calls"] >= b["scans"] - 1
+    # ScanSolver::getGraph() of the adapter (the node store the toolbox visualises): one finite pose per vertex
+    assert b["graph_nodes"] == b["scans"] and len(np.unique(b["graph_ids"])) == b["scans"] and np.isfinite(b["graph_poses"]).all()
     # the published map (SMapper::getOccupancyGrid): b200og binding == the reference's OccupancyGrid::CreateFromScans
     assert b["map_cpu_seconds"] >= 0 and b["map_gpu_seconds"] >= 0
     assert np.array_equal(b["map_cpu_dims"], b["map_gpu_dims"]) and np.array_equal(b["map_cpu_offset"], b["map_gpu_offset"])

@@ -141,14 +141,25 @@ int b200sm_batch_best(b200sm * h, int32_t * best_sum, int32_t * best_index, int3
  * caller hands to ncclAllReduce(ncclMax) / torch.distributed.all_reduce(MAX) next), on the
  * handle's stream. A max over ranks selects the highest sum, ties to the lowest global id. */
 int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset);
-/* Which kernel the uploaded sweep will run on and how its lookups were classified: info = {fast path (1) or generic (0),
- * FAST descriptors, EDGE beams (window leaves the grid), FAR beams (column offset >= one stride), reason code when the fast path was refused (0 = n/a), CTAs, pairs, items}. */
+/* Which kernel the uploaded sweep will run on and how its lookups were classified: info = {kernel: 0 generic, 1 single-CTA
+ * shared-memory kernel (search <= 48 x 48 poses, grid <= 576 cells), 2 tiled cluster kernel (any search size / range threshold);
+ * FAST descriptors, EDGE beams (window leaves the grid), FAR beams (column offset >= one stride), reason code when the
+ * shared-memory paths were refused (0 = n/a), CTAs, pairs, items}. */
 int b200sm_batch_info(b200sm * h, int32_t info[8]);
+/* Plan of the tiled cluster kernel for the uploaded sweep: info = {available, cluster size (CTAs per pair), angle chunks,
+ * sub-grid bands per parity phase, rows per band, refusal reason, resident clusters, shared memory per CTA (KB)}. */
+int b200sm_batch_tile_info(b200sm * h, int32_t info[8]);
+/* How the last fetch finished its pairs: stats = {pairs whose volume was all zero (all poses tie: closed form, once per
+ * query), pairs handed one by one to the single-match path (tie list overflow with a non-zero best, response expansion),
+ * pairs, 0}. */
+int b200sm_batch_fetch_stats(b200sm * h, int32_t stats[4]);
 /* bytes copied host->device by upload and device->host by fetch since the last reset */
 int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_bytes, int32_t reset);
 /* Tuning / testing switches. "force_generic_sweep" = 1 runs batched sweeps on the generic kernel even
  * where the shared-memory fast path applies; "no_beam_dedup" = 1 keeps one lookup descriptor per beam in the fast
- * path instead of merging beams that hit the same cell (all variants produce identical results). */
+ * path instead of merging beams that hit the same cell; "sweep_kernel" = 0 auto / 1 single-CTA kernel / 2 tiled cluster
+ * kernel; "sweep_cluster" = CTAs per pair of the tiled kernel (0 auto, 1, 2, 4, 8); "sweep_chunks" = angle chunks (0 auto).
+ * All variants produce identical results. */
 int b200sm_set_option(b200sm * h, const char * name, int32_t value);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t b200sm_launch_count(const b200sm * h);
@@ -193,6 +204,9 @@ typedef struct b200pg_summary {
   double initial_cost, final_cost;
   float solve_ms;              /* device time of the whole solve (CUDA events)         */
   int64_t kernel_launches;
+  float setup_ms;              /* host time before the first kernel: flatten / adjacency / uploads of what changed */
+  float wall_ms;               /* host wall time of the whole call                     */
+  int32_t uploaded_edges;      /* constraints copied to the device by this call (the ones added since the last solve) */
 } b200pg_summary;
 
 typedef struct b200pg b200pg;

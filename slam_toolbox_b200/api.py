@@ -70,7 +70,8 @@ class OgInfo(C.Structure):
 class PgSummary(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("successful_steps", C.c_int32), ("pcg_iterations", C.c_int32),
                 ("termination", C.c_int32), ("usable", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
-                ("solve_ms", C.c_float), ("kernel_launches", C.c_int64)]
+                ("solve_ms", C.c_float), ("kernel_launches", C.c_int64),
+                ("setup_ms", C.c_float), ("wall_ms", C.c_float), ("uploaded_edges", C.c_int32)]
 
 
 def library_path() -> str:
@@ -107,6 +108,8 @@ def lib():
     L.b200sm_batch_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.b200sm_batch_best.argtypes = [C.c_void_p, _IP, _IP, _IP]
     L.b200sm_batch_info.argtypes = [C.c_void_p, _IP]
+    L.b200sm_batch_tile_info.argtypes = [C.c_void_p, _IP]
+    L.b200sm_batch_fetch_stats.argtypes = [C.c_void_p, _IP]
     L.b200sm_batch_reduce_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.b200sm_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]
     L.b200sm_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
@@ -356,8 +359,20 @@ class ScanMatcher:
     def batch_info(self):
         info = np.zeros(8, dtype=np.int32)
         _check(lib().b200sm_batch_info(self._h, _ip(info)))
-        return dict(fast=bool(info[0]), fast_descriptors=int(info[1]), edge_beams=int(info[2]), far_beams=int(info[3]),
+        return dict(fast=bool(info[0]), kernel=("generic", "fast", "tile")[int(info[0])], fast_descriptors=int(info[1]), edge_beams=int(info[2]), far_beams=int(info[3]),
                     refused_reason=int(info[4]), ctas=int(info[5]), pairs=int(info[6]), items=int(info[7]))
+
+    def batch_tile_info(self):
+        """Plan of the tiled cluster kernel for the uploaded sweep (b200sm_batch_tile_info)."""
+        info = np.zeros(8, dtype=np.int32)
+        _check(lib().b200sm_batch_tile_info(self._h, _ip(info)))
+        return dict(available=bool(info[0]), cluster=int(info[1]), chunks=int(info[2]), bands=int(info[3]), band_rows=int(info[4]),
+                    refused_reason=int(info[5]), clusters=int(info[6]), smem_kb=int(info[7]))
+
+    def batch_fetch_stats(self):
+        st = np.zeros(4, dtype=np.int32)
+        _check(lib().b200sm_batch_fetch_stats(self._h, _ip(st)))
+        return dict(zero_pairs=int(st[0]), fallback_pairs=int(st[1]), pairs=int(st[2]))
 
     def transfer_bytes(self, reset: bool = False):
         a, b = C.c_int64(), C.c_int64()

@@ -21,6 +21,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -1196,6 +1197,14 @@ struct b200pg {
   std::vector<PgEdge> edges;
   int32_t first_node_id = 0;
   bool have_first = false;
+  // flattened edge arrays (node positions, measurement, sqrt information), kept in step with `edges`: AddConstraint appends
+  // (the mapper's normal traffic, Mapper.cpp:1634), removals / Reset mark them for a rebuild.  dev_edges of them are already
+  // on the device, so a Compute after k new constraints uploads k edges, not the graph.
+  std::vector<int32_t> f_eidx;
+  std::vector<double> f_z, f_U;
+  bool flat_dirty = false;
+  size_t dev_edges = 0;
+  std::vector<int32_t> agg_start_h, agg_of_h;
   // corrections of the last solve
   std::vector<int32_t> corr_ids;
   std::vector<double> corr_pose;
@@ -1278,6 +1287,19 @@ static void up(DevBuf<T> & dst, const std::vector<T> & src, cudaStream_t s)
   if (!src.empty()) B200_CUDA(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s));
 }
 
+// grow a device buffer to n elements keeping its first `keep` ones
+template <class T>
+static void grow_keep(DevBuf<T> & b, size_t n, size_t keep, cudaStream_t s)
+{
+  if (n <= b.cap) return;
+  if (keep == 0 || !b.p) { b.reserve(n); return; }
+  DevBuf<T> nb;
+  nb.reserve(n + n / 2);
+  B200_CUDA(cudaMemcpyAsync(nb.p, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  std::swap(b.p, nb.p); std::swap(b.cap, nb.cap);
+}
+
 struct Lm {
   b200pg * h;
   PgDev d;
@@ -1322,6 +1344,7 @@ struct Lm {
 
 static int solve(b200pg * h, b200pg_summary * sum)
 {
+  const auto t_enter = std::chrono::steady_clock::now();
   const b200pg_opts & o = h->o;
   b200pg_summary S{};
   S.usable = 1;
@@ -1337,18 +1360,24 @@ static int solve(b200pg * h, b200pg_summary * sum)
   if (!h->ev0) { B200_CUDA(cudaEventCreate(&h->ev0)); B200_CUDA(cudaEventCreate(&h->ev1)); }
   const int64_t launches0 = h->launches;
 
-  // ---- flatten the graph ----
+  // ---- flattened graph: kept incrementally (see b200pg::f_eidx) ----
   const int E = (int)h->edges.size();
-  std::vector<int32_t> eidx(2 * (size_t)E);
-  std::vector<double> z(3 * (size_t)E), U(6 * (size_t)E);
+  if (h->flat_dirty || h->f_eidx.size() != 2 * (size_t)E) {
+    h->f_eidx.resize(2 * (size_t)E); h->f_z.resize(3 * (size_t)E); h->f_U.resize(6 * (size_t)E);
+    for (int e = 0; e < E; ++e) {
+      const PgEdge & ed = h->edges[e];
+      h->f_eidx[2 * e] = h->index.at(ed.ida); h->f_eidx[2 * e + 1] = h->index.at(ed.idb);
+      for (int k = 0; k < 3; ++k) h->f_z[3 * e + k] = ed.z[k];
+      for (int k = 0; k < 6; ++k) h->f_U[6 * e + k] = ed.U[k];
+    }
+    h->flat_dirty = false;
+    h->dev_edges = 0;
+  }
+  const std::vector<int32_t> & eidx = h->f_eidx;
   std::vector<uint8_t> is_free(N, 0);
   std::vector<int32_t> deg(N + 1, 0);
   for (int e = 0; e < E; ++e) {
-    const PgEdge & ed = h->edges[e];
-    int a = h->index.at(ed.ida), b = h->index.at(ed.idb);
-    eidx[2 * e] = a; eidx[2 * e + 1] = b;
-    for (int k = 0; k < 3; ++k) z[3 * e + k] = ed.z[k];
-    for (int k = 0; k < 6; ++k) U[6 * e + k] = ed.U[k];
+    const int a = eidx[2 * e], b = eidx[2 * e + 1];
     is_free[a] = 1; is_free[b] = 1;   // only nodes that appear in a residual block are Ceres parameter blocks
     deg[a + 1]++; deg[b + 1]++;
   }
@@ -1378,7 +1407,20 @@ static int solve(b200pg * h, b200pg_summary * sum)
       adj[fill[eidx[2 * e + 1]]++] = (e << 1) | 1;
     }
   }
-  up(h->d_eidx, eidx, st); up(h->d_z, z, st); up(h->d_U, U, st); up(h->d_free, is_free, st);
+  {
+    // edges: only the ones appended since the last solve travel (the buffers grow with their contents kept)
+    if (h->dev_edges > (size_t)E) h->dev_edges = 0;
+    const size_t e0 = h->dev_edges, ne = (size_t)E - e0;
+    grow_keep(h->d_eidx, 2 * (size_t)E, 2 * e0, st); grow_keep(h->d_z, 3 * (size_t)E, 3 * e0, st); grow_keep(h->d_U, 6 * (size_t)E, 6 * e0, st);
+    if (ne) {
+      B200_CUDA(cudaMemcpyAsync(h->d_eidx.p + 2 * e0, h->f_eidx.data() + 2 * e0, 2 * ne * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      B200_CUDA(cudaMemcpyAsync(h->d_z.p + 3 * e0, h->f_z.data() + 3 * e0, 3 * ne * sizeof(double), cudaMemcpyHostToDevice, st));
+      B200_CUDA(cudaMemcpyAsync(h->d_U.p + 6 * e0, h->f_U.data() + 6 * e0, 6 * ne * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    S.uploaded_edges = (int32_t)ne;
+    h->dev_edges = (size_t)E;
+  }
+  up(h->d_free, is_free, st);
   up(h->d_adj_start, adj_start, st); up(h->d_adj, adj, st); up(h->d_x, h->node_pose, st);
   const size_t n3 = 3 * (size_t)N;
   h->d_xc.reserve(n3); h->d_scale.reserve(n3); h->d_lin.reserve((size_t)kLin * E); h->d_Hd.reserve(6 * (size_t)N);
@@ -1431,7 +1473,9 @@ static int solve(b200pg * h, b200pg_summary * sum)
       const int G2 = std::min(per_sm * sms, std::max(1, (N + 15) / 16));
       // contiguous node ranges of equal node count: compact aggregates give the best coarse space (balancing by
       // block count was tried: it merges sparse chain stretches into large aggregates and costs 60 % more iterations)
-      std::vector<int32_t> agg_start, agg_of(N);
+      std::vector<int32_t> & agg_start = h->agg_start_h;
+      std::vector<int32_t> & agg_of = h->agg_of_h;
+      agg_start.clear(); agg_of.assign(N, 0);
       {
         const int per = (N + G2 - 1) / G2;
         for (int i = 0; i < N; i += per) agg_start.push_back(i);
@@ -1470,14 +1514,14 @@ static int solve(b200pg * h, b200pg_summary * sum)
       h->d_bar.reserve(std::max<size_t>(4096, (size_t)Gu + 4));
       h->d_gPt.reserve(10 * (size_t)N); h->d_gRow.reserve((size_t)Gu * cm * 2 * nc); h->d_grc.reserve(nc);
       h->d_e1.reserve((size_t)2 * Gu * kSlotStride); h->d_e2.reserve((size_t)2 * Gu * kSlotStride);
-      up(h->d_agg_start, agg_start, st); up(h->d_agg_of, agg_of, st);
-      B200_CUDA(cudaStreamSynchronize(st));   // the two vectors go out of scope
+      up(h->d_agg_start, agg_start, st); up(h->d_agg_of, agg_of, st);   // the vectors live in the handle
       Pcg2Cfg & c2 = L.cfg2;
       c2.npc = npc; c2.max_slots = max_slots; c2.ex_doubles = ex_doubles; c2.agg_start = h->d_agg_start.p; c2.agg_of = h->d_agg_of.p;
       c2.gz = h->d_gz.p; c2.gp = h->d_gp.p; c2.gPt = h->d_gPt.p; c2.gRow = h->d_gRow.p;
       c2.grc = h->d_grc.p; c2.e1 = h->d_e1.p; c2.e2 = h->d_e2.p; c2.bar = h->d_bar.p; c2.gjflag = h->d_bar.p + 1;
     }
   }
+  S.setup_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
   B200_CUDA(cudaEventRecord(h->ev0, st));
   // ---- iteration 0: evaluate, Jacobi scaling from the unscaled Jacobian ----
   k_pg_fill<<<64, 256, 0, st>>>(d.scale, 1.0, 3 * N); L.launched();
@@ -1598,6 +1642,7 @@ static int solve(b200pg * h, b200pg_summary * sum)
   B200_CUDA(cudaStreamSynchronize(st));
   B200_CUDA(cudaEventElapsedTime(&S.solve_ms, h->ev0, h->ev1));
   S.kernel_launches = h->launches - launches0;
+  S.wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_enter).count();
   if (sum) *sum = S;
   if (!S.usable) {
     set_last_error("pose-graph solve produced no usable solution (too many invalid steps)");
@@ -1668,6 +1713,7 @@ int b200pg_reset(b200pg * h)
   h->node_ids.clear(); h->node_pose.clear(); h->index.clear(); h->edges.clear();
   h->corr_ids.clear(); h->corr_pose.clear();
   h->have_first = false;
+  h->f_eidx.clear(); h->f_z.clear(); h->f_U.clear(); h->flat_dirty = false; h->dev_edges = 0;
   return B200_OK;
 }
 
@@ -1704,6 +1750,11 @@ int b200pg_add_edge(b200pg * h, int32_t ida, int32_t idb, const double z[3], con
     return B200_ERR_NUMERIC;
   }
   h->edges.push_back(e);
+  if (!h->flat_dirty) {
+    h->f_eidx.push_back(h->index[ida]); h->f_eidx.push_back(h->index[idb]);
+    h->f_z.insert(h->f_z.end(), e.z, e.z + 3);
+    h->f_U.insert(h->f_U.end(), e.U, e.U + 6);
+  }
   return B200_OK;
 }
 
@@ -1716,6 +1767,7 @@ int b200pg_remove_node(b200pg * h, int32_t id)
   h->edges.erase(std::remove_if(h->edges.begin(), h->edges.end(), [&](const PgEdge & e) { return e.ida == id || e.idb == id; }),
                  h->edges.end());
   const int pos = it->second, last = (int)h->node_ids.size() - 1;
+  h->flat_dirty = true;   // node positions move and edges go: the flattened arrays are rebuilt by the next solve
   h->index.erase(it);
   if (pos != last) {
     h->node_ids[pos] = h->node_ids[last];
@@ -1736,6 +1788,7 @@ int b200pg_remove_edge(b200pg * h, int32_t ida, int32_t idb)
       const PgEdge & e = h->edges[k];
       if ((pass == 0 && e.ida == ida && e.idb == idb) || (pass == 1 && e.ida == idb && e.idb == ida)) {
         h->edges.erase(h->edges.begin() + k);
+        h->flat_dirty = true;
         return B200_OK;
       }
     }

@@ -757,6 +757,9 @@ int b200sm_set_option(b200sm * h, const char * name, int32_t value)
   if (!h || !name) return B200_ERR_INVALID_ARG;
   if (std::string(name) == "force_generic_sweep") { h->force_generic = value != 0; return B200_OK; }
   if (std::string(name) == "no_beam_dedup") { h->no_dedup = value != 0; return B200_OK; }
+  if (std::string(name) == "sweep_kernel") { h->sweep_kernel = value; return B200_OK; }
+  if (std::string(name) == "sweep_cluster") { h->tile_cluster = value; return B200_OK; }
+  if (std::string(name) == "sweep_chunks") { h->tile_chunks = value; return B200_OK; }
   set_last_error(std::string("unknown option ") + name);
   return B200_ERR_INVALID_ARG;
 }

@@ -17,6 +17,7 @@
 #include "sm_math.cuh"
 #include "sm_types.cuh"
 #include "sm_device.cuh"
+#include "sm_sweep_dev.cuh"
 
 namespace b200 {
 
@@ -108,61 +109,6 @@ __global__ void __launch_bounds__(kFvWarps * 32) k_find_valid(SweepDev d)
     total += __popc(m);
   }
   if (lane == 0) d.cell_count[item] = total;
-}
-
-__device__ __forceinline__ double block_max(double v, double * scratch)
-{
-  for (int o = 16; o > 0; o >>= 1) {
-    double other = __shfl_xor_sync(0xffffffffu, v, o);
-    v = other > v ? other : v;
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-  double r = scratch[0];
-  for (int i = 1; i < nw; ++i) r = scratch[i] > r ? scratch[i] : r;
-  __syncthreads();
-  return r;
-}
-
-// exclusive prefix sum of one int per thread over the block; returns the exclusive value and
-// writes the block total
-__device__ __forceinline__ int block_exclusive_scan(int v, int * scratch, int & total)
-{
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = v;
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  __syncthreads();
-  if (lane == 31) scratch[warp] = inc;
-  __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-  int base = 0, tot = 0;
-  for (int i = 0; i < nw; ++i) {
-    if (i < warp) base += scratch[i];
-    tot += scratch[i];
-  }
-  __syncthreads();
-  total = tot;
-  return base + inc - v;
-}
-
-// response of pose (xy, a) from its integer sum, exactly as ScanMatcher::operator() builds it
-// (M.cpp:670-685)
-__device__ __forceinline__ double pose_response(const SweepDev & d, int q, int sum, int x, int y, int a)
-{
-  double r = (double)sum;
-  r /= d.norm;
-  if (d.do_penalize && !double_equal(r, 0.0)) {
-    double dp = distance_penalty(d.sqx[q * d.nX + x], d.sqy[q * d.nY + y], d.dist_var, d.min_dist_pen);
-    double ap = d.angpen[q * d.nA + a];
-    r *= (dp * ap);
-  }
-  return r;
 }
 
 // The on-device part of CorrelateScan's reduction (M.cpp:775-829) and of
@@ -732,6 +678,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
 {
   SweepHost & S = h->sweep;
   S.uploaded = S.ran = false;
+  S.zero_done.clear();
   g_h2d_counter = &S.h2d_bytes;
   if (!queries || nq <= 0 || !scans || nscans <= 0 || !chain_start || nchains <= 0) {
     set_last_error("sweep: empty or NULL input");
@@ -917,6 +864,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   if (!S.ev0) { B200_CUDA(cudaEventCreate(&S.ev0)); B200_CUDA(cudaEventCreate(&S.ev1)); }
   B200_CUDA(cudaStreamSynchronize(st));
   build_fast_tables(h, S, st);
+  build_tile_tables(h, S, st);
   S.uploaded = true;
   return B200_OK;
 }
@@ -1064,6 +1012,19 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   return true;
 }
 
+// which kernel an uploaded sweep runs on: 0 = generic (any geometry), 1 = single-CTA fast kernel (BASELINE's 4 m / 12 m
+// geometry), 2 = tiled cluster kernel (any even-stride geometry whose raster is order independent)
+static int sweep_kernel_choice(const b200sm * h, const SweepHost & S)
+{
+  if (h->force_generic) return 0;
+  const bool fast = S.fast.enabled != 0, tile = S.tile.enabled != 0;
+  if (h->sweep_kernel == 1 && fast) return 1;
+  if (h->sweep_kernel == 2 && tile) return 2;
+  if (tile && (!fast || S.tile.C > 1)) return 2;   // small batches: spread a pair over a cluster
+  if (fast) return 1;
+  return tile ? 2 : 0;
+}
+
 static int sweep_run(b200sm * h)
 {
   SweepHost & S = h->sweep;
@@ -1081,13 +1042,19 @@ static int sweep_run(b200sm * h)
     h->launches++;
   }
   B200_CUDA(cudaEventRecord(S.ev0, st));
-  if (S.fast.enabled && !h->force_generic) {
-    B200_CUDA(cudaFuncSetAttribute(k_sweep_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.fast_smem));
-    k_sweep_fast<<<S.fast_blocks, kFastThreads, S.fast_smem, st>>>(d, S.fast);
-  } else {
-    const size_t smem = (size_t)d.nA * d.n * sizeof(int32_t);
-    B200_CUDA(cudaFuncSetAttribute(k_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sweep_generic<<<S.blocks, kSweepThreads, smem, st>>>(d);
+  switch (sweep_kernel_choice(h, S)) {
+    case 2:
+      launch_sweep_tile(h, S, st);
+      break;
+    case 1:
+      B200_CUDA(cudaFuncSetAttribute(k_sweep_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.fast_smem));
+      k_sweep_fast<<<S.fast_blocks, kFastThreads, S.fast_smem, st>>>(d, S.fast);
+      break;
+    default: {
+      const size_t smem = (size_t)d.nA * d.n * sizeof(int32_t);
+      B200_CUDA(cudaFuncSetAttribute(k_sweep_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_sweep_generic<<<S.blocks, kSweepThreads, smem, st>>>(d);
+    }
   }
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaEventRecord(S.ev1, st));
@@ -1096,13 +1063,45 @@ static int sweep_run(b200sm * h)
   return B200_OK;
 }
 
+// A pair whose whole correlation volume is zero (the candidate does not overlap the query's search window): every pose
+// ties at response 0, so CorrelateScan averages ALL poses in array order (M.cpp:802-829) and the covariance is the
+// "no response" one (M.cpp:886-891).  The result depends on the query's plan only: computed once per query, in the
+// reference's summation order (cos / sin of the 21 headings evaluated once each -- same inputs, same libm results).
+static void zero_volume_result(const CorrPlan & pl, double mean[3], double cov[9])
+{
+  std::vector<double> ch(pl.nA), shd(pl.nA);
+  for (int a = 0; a < pl.nA; ++a) { ch[a] = cos(pl.heading[a]); shd[a] = sin(pl.heading[a]); }
+  double ax = 0.0, ay = 0.0, thetaX = 0.0, thetaY = 0.0;
+  for (int y = 0; y < pl.nY; ++y)
+    for (int x = 0; x < pl.nX; ++x)
+      for (int a = 0; a < pl.nA; ++a) {
+        ax += pl.newx[x]; ay += pl.newy[y];
+        thetaX += ch[a]; thetaY += shd[a];
+      }
+  const int icount = pl.nX * pl.nY * pl.nA;
+  ax /= icount; ay /= icount; thetaX /= icount; thetaY /= icount;
+  mean[0] = ax; mean[1] = ay; mean[2] = atan2(thetaY, thetaX);
+  for (int i = 0; i < 9; ++i) cov[i] = 0.0;
+  cov[0] = kMaxVariance; cov[4] = kMaxVariance; cov[8] = 4 * square(pl.ang_res);
+}
+
 // finish one pair on the host from the device reduction: heading average (libm) + covariance tail
-static bool finish_pair(const b200sm * h, const SweepHost & S, int pair, const PairOut & o, double * response,
+static bool finish_pair(const b200sm * h, SweepHost & S, int pair, const PairOut & o, double * response,
                         double * mean, double * cov)
 {
-  const CorrPlan & pl = S.plans[S.pair_query[pair]];
-  if (o.tie_count <= 0 || o.tie_count > kMaxTies) return false;
+  const int q = S.pair_query[pair];
+  const CorrPlan & pl = S.plans[q];
   if (h->p.use_response_expansion && double_equal(o.best, 0.0)) return false;   // M.cpp:594-619 needs more passes
+  if (o.best == 0.0 && o.tie_count == pl.nX * pl.nY * pl.nA && o.tie_count > kMaxTies) {
+    if ((int)S.zero_done.size() != S.nq) { S.zero_done.assign(S.nq, 0); S.zero_mean.assign((size_t)3 * S.nq, 0.0); S.zero_cov.assign((size_t)9 * S.nq, 0.0); }
+    if (!S.zero_done[q]) { zero_volume_result(pl, &S.zero_mean[3 * (size_t)q], &S.zero_cov[9 * (size_t)q]); S.zero_done[q] = 1; }
+    for (int i = 0; i < 3; ++i) mean[i] = S.zero_mean[3 * (size_t)q + i];
+    for (int i = 0; i < 9; ++i) cov[i] = S.zero_cov[9 * (size_t)q + i];
+    *response = 0.0;
+    S.zero_pairs++;
+    return true;
+  }
+  if (o.tie_count <= 0 || o.tie_count > kMaxTies) return false;
   double thetaX = 0.0, thetaY = 0.0;
   for (int t = 0; t < o.tie_count; ++t) {   // M.cpp:811-813
     double heading = pl.heading[o.ties[t] % pl.nA];
@@ -1138,6 +1137,7 @@ static int sweep_fetch(b200sm * h, bool do_refine, double * response, double * m
   B200_CUDA(cudaStreamSynchronize(st));
   S.d2h_bytes += (int64_t)((size_t)S.npairs * sizeof(PairOut));
   std::vector<char> done(S.npairs, 0);
+  S.zero_pairs = S.fallback_pairs = 0;
   for (int p = 0; p < S.npairs; ++p) {
     if (!finish_pair(h, S, p, S.h_out.p[p], &response[p], &mean[3 * p], &cov[9 * p])) {
       // tie-list overflow / response expansion: this pair goes through the single-match path
@@ -1145,6 +1145,7 @@ static int sweep_fetch(b200sm * h, bool do_refine, double * response, double * m
       chain_of_pair(S, p, base, nbase);
       response[p] = do_match(h, &S.queries[S.pair_query[p]], base, nbase, S.do_penalize, do_refine, &mean[3 * p], &cov[9 * p]);
       done[p] = 1;
+      S.fallback_pairs++;
     }
   }
   if (!do_refine) return B200_OK;
@@ -1276,10 +1277,27 @@ int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset)
 int b200sm_batch_info(b200sm * h, int32_t info[8])
 {
   if (!h || !info || !h->sweep.uploaded) return B200_ERR_INVALID_ARG;
-  for (int i = 0; i < 5; ++i) info[i] = h->sweep.fast_info[i];
-  info[0] = (h->sweep.fast.enabled && !h->force_generic) ? 1 : 0;
-  info[5] = h->sweep.fast.enabled ? h->sweep.fast_blocks : h->sweep.blocks;
-  info[6] = h->sweep.npairs; info[7] = h->sweep.nitems;
+  const SweepHost & S = h->sweep;
+  const int k = sweep_kernel_choice(h, S);
+  for (int i = 0; i < 5; ++i) info[i] = S.fast_info[i];
+  info[0] = k;
+  if (k == 2) info[4] = 0; else if (k == 0 && S.tile_info[5]) info[4] = 100 + S.tile_info[5];
+  info[5] = k == 2 ? S.tile_grid : (k == 1 ? S.fast_blocks : S.blocks);
+  info[6] = S.npairs; info[7] = S.nitems;
+  return B200_OK;
+}
+
+int b200sm_batch_tile_info(b200sm * h, int32_t info[8])
+{
+  if (!h || !info || !h->sweep.uploaded) return B200_ERR_INVALID_ARG;
+  for (int i = 0; i < 8; ++i) info[i] = h->sweep.tile_info[i];
+  return B200_OK;
+}
+
+int b200sm_batch_fetch_stats(b200sm * h, int32_t stats[4])
+{
+  if (!h || !stats) return B200_ERR_INVALID_ARG;
+  stats[0] = h->sweep.zero_pairs; stats[1] = h->sweep.fallback_pairs; stats[2] = h->sweep.npairs; stats[3] = 0;
   return B200_OK;
 }
 

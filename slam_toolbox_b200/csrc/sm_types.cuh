@@ -139,6 +139,40 @@ struct FastDev {
   const int32_t * slow_start;    // [nq][nA + 1]
 };
 
+// Tiled sweep path (k_sweep_tile, sm_tile.cu): the generalisation of the fast path to any search
+// dimension / range threshold.  A pair's pose volume is cut into V angle CHUNKS (accumulators of one
+// chunk in shared memory) that are spread over the C CTAs of a thread-block cluster; the parity
+// sub-grid is cut into row BANDS so that one band + one chunk fit an SM.  The per-(chunk, phase,
+// band) beam-descriptor blocks are streamed into shared memory with cp.async.bulk + mbarrier.
+constexpr int kTileThreads = 1024;
+constexpr int kTileMaxCluster = 8;
+struct TileSeq {                 // one descriptor block of a query's schedule (16 bytes)
+  int32_t off;                   // byte offset in the descriptor blob (16-byte aligned)
+  int32_t bytes;                 // size, multiple of 16
+  int16_t chunk, stage;          // angle chunk; stage = phase * nbands + band
+  int16_t a0, na;                // angles [a0, a0 + na) of this block (global indices)
+  uint32_t flags;                // kSeq* bits
+};
+constexpr uint32_t kSeqNewChunk = 1, kSeqNewStage = 2, kSeqEndChunk = 4;
+struct TileDev {
+  int enabled;
+  int C, V, nAc;                 // cluster size, angle chunks, angles per chunk
+  int nbands, band_rows, alloc_rows, pitch_w;   // sub-grid banding (rows of one parity), allocated rows, row pitch in words
+  int xtiles, ytiles;
+  int stage_bytes;               // size of one descriptor staging buffer
+  int int_ties;                  // responses are monotone in the integer sum with spacing > tolerance: integer arg-max / ties
+  size_t off_A, off_probs, off_stage;   // byte offsets into dynamic shared memory (S at 0)
+  const uint8_t * desc;          // descriptor blob
+  const TileSeq * seq;           // schedules
+  const int32_t * seq_start;     // [nq * C + 1]
+  const int32_t * edge;          // EDGE beams: band-relative sub-row | word << 16
+  const int32_t * edge_start;    // CSR over ((q * nA + a) * 4 * nbands + stage) * 4 + m
+  const int32_t * wrap2;         // EDGE beams whose columns wrap into a neighbouring row
+  const int32_t * wrap2_start;   // CSR over (q * nA + a) * 4 * nbands + stage
+  const int32_t * slow;          // FAR beams (device-form linear offsets)
+  const int32_t * slow_start;    // [nq][nA + 1]
+};
+
 struct FineDev {
   int P, nA;
   const int32_t * offsets;   // [npairs][nA][n]
@@ -164,6 +198,13 @@ struct SweepHost {
   DevBuf<int32_t> d_fast_cls, d_fast_slow, d_fast_slow_start, d_fast_wrap2, d_fast_wrap2_start, d_fast_edge, d_fast_edge_start;
   FastDev fast{};
   size_t fast_smem = 0;
+  TileDev tile{};
+  size_t tile_smem = 0;
+  int tile_grid = 0;
+  int32_t tile_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // enabled, C, V, nbands, band rows, refusal reason, clusters, smem KB
+  DevBuf<uint8_t> d_tile_desc;
+  DevBuf<TileSeq> d_tile_seq;
+  DevBuf<int32_t> d_tile_seq_start, d_tile_edge, d_tile_edge_start, d_tile_wrap2, d_tile_wrap2_start, d_tile_slow, d_tile_slow_start;
   int32_t fast_info[5] = {0, 0, 0, 0, 0};   // enabled, FAST descriptors, CLIP beams, WRAP beams, reason the fast path was refused
   int fast_blocks = 0;
   DevBuf<PairOut> d_out;
@@ -173,6 +214,10 @@ struct SweepHost {
   SweepDev dev{};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes moved by upload / fetch since the last reset
+  // pairs of the last fetch finished by the all-poses-tie closed form / handed to the single-match path
+  int zero_pairs = 0, fallback_pairs = 0;
+  std::vector<char> zero_done;
+  std::vector<double> zero_mean, zero_cov;
   void release();
 };
 
@@ -195,6 +240,9 @@ struct b200sm {
   b200::CellScratch cell_scratch;
   bool no_dedup = false;        // testing: keep one descriptor per beam in the fast sweep lists
   bool force_generic = false;   // testing: run sweeps on the generic kernel even when the fast path applies
+  int sweep_kernel = 0;         // 0 = auto, 1 = legacy single-CTA fast kernel when it applies, 2 = tiled cluster kernel
+  int tile_cluster = 0;         // 0 = auto, else forced cluster size (1, 2, 4, 8)
+  int tile_chunks = 0;          // 0 = auto, else forced number of angle chunks
 
   b200::SweepHost sweep;
 
@@ -219,6 +267,8 @@ double normalize_angle_difference(double minuend, double subtrahend);
 
 namespace b200 {
 // ScanMatcher::CorrelateScan's reduction + covariance (M.cpp:775-1025) on the host from an integer volume
+bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st);
+void launch_sweep_tile(b200sm * h, SweepHost & S, cudaStream_t st);
 double host_epilogue(const b200sm_params & prm, const GridGeom & geom, int probs_side, const CorrPlan & pl,
                      const int32_t * sums, bool do_penalize, double mean[3], double cov[9]);
 }  // namespace b200

@@ -1,0 +1,100 @@
+"""The tiled cluster sweep kernel (csrc/sm_tile.cu) on the reference's shipped loop-closure geometries:
+loop_search_space_dimension 8 m (config/mapper_params_online_sync.yaml:61, Mapper.cpp:2231 -> 81 x 81 x 21 poses),
+max_laser_range 20 m (:32 -> 885..965-cell correlation grids), and BASELINE's 4 m / 12 m -- every cluster size and several
+chunkings, bit-exact against the oracle (C restatement pinned to the reference) and against the generic kernel."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from slam_toolbox_b200 import synth
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+GRID_DIM8 = (8.0, 0.05, 0.03, 12.0)
+GRID_RT20 = (4.0, 0.05, 0.03, 20.0)
+GRID_DIM8_RT20 = (8.0, 0.05, 0.03, 20.0)
+
+
+def _expected(pm, sw, nq, nch, pen=False):
+    pc, pq = H.port_scans(sw.cand_ranges, sw.cand_poses), H.port_scans(sw.query_ranges, sw.query_poses)
+    exp = [pm.match(pq[q], pc[sw.chain_start[c]:sw.chain_start[c + 1]], pen, False) for q in range(nq) for c in range(nch)]
+    return np.array([e[0] for e in exp]), np.array([e[1] for e in exp]), np.array([e[2] for e in exp])
+
+
+def _run(gm, gq, gc, sw, pen=False):
+    r, m, c = gm.MatchScanBatch(gq, gc, sw.chain_start, None, pen, False)
+    return r, m, c, gm.batch_best()
+
+
+@pytest.mark.parametrize("grid,seed", [(H.GRID_LOOP, 31), (GRID_DIM8, 32), (GRID_RT20, 33), (GRID_DIM8_RT20, 34),
+                                       ((4.0, 0.05, 0.03, 6.0), 35), ((2.0, 0.05, 0.05, 8.0), 36)])
+def test_tile_kernel_every_cluster_size_vs_oracle(grid, seed):
+    nq, nch = 2, 6
+    sw = synth.make_loop_sweep(seed, n_queries=nq, n_chains=nch, chain_len=2, inf_frac=0.02)
+    mapper = dict(H.MAPPER_LOOP, use_response_expansion=0)
+    pm, gm = H.port_matcher(mapper, grid), H.gpu_matcher(mapper, grid)
+    gc, gq = H.gpu_block(sw.cand_ranges, sw.cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
+    er, em, ec = _expected(pm, sw, nq, nch)
+    gm.set_option("force_generic_sweep", 1)
+    gen = _run(gm, gq, gc, sw)
+    gm.set_option("force_generic_sweep", 0)
+    assert np.array_equal(gen[0], er) and np.array_equal(gen[1], em) and np.array_equal(gen[2], ec)
+    gm.set_option("sweep_kernel", 2)
+    plans = set()
+    for cluster, chunks in ((1, 0), (2, 0), (4, 0), (8, 0), (1, 21), (2, 5), (4, 11), (0, 0)):
+        gm.set_option("sweep_cluster", cluster)
+        gm.set_option("sweep_chunks", chunks)
+        out = _run(gm, gq, gc, sw)
+        info, plan = gm.batch_info(), gm.batch_tile_info()
+        assert info["kernel"] == "tile" and plan["available"], (info, plan)
+        if cluster:
+            assert plan["cluster"] == cluster, plan
+        plans.add((plan["cluster"], plan["chunks"], plan["bands"]))
+        assert np.array_equal(out[0], er), (plan, out[0], er)
+        assert np.array_equal(out[1], em) and np.array_equal(out[2], ec), plan
+        for a, b in zip(out[3], gen[3]):     # best integer sum, arg-max pose index, tie count
+            assert np.array_equal(a, b), plan
+    assert len(plans) >= 4, plans
+    if grid[3] < 12.0:
+        assert gm.batch_info()["edge_beams"] > 0
+
+
+def test_tile_kernel_with_penalties_and_single_scans():
+    """FP64 response path (doPenalize) of the distributed reduction: chunk bests within the tie tolerance fall back, everything
+    else is reduced on the device; chain length 1."""
+    nq, nch = 2, 8
+    sw = synth.make_loop_sweep(41, n_queries=nq, n_chains=nch, chain_len=1)
+    mapper = dict(H.MAPPER_LOOP, use_response_expansion=0)
+    pm, gm = H.port_matcher(mapper, GRID_DIM8), H.gpu_matcher(mapper, GRID_DIM8)
+    gc, gq = H.gpu_block(sw.cand_ranges, sw.cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
+    er, em, ec = _expected(pm, sw, nq, nch, pen=True)
+    gm.set_option("sweep_kernel", 2)
+    for cluster in (1, 4):
+        gm.set_option("sweep_cluster", cluster)
+        r, m, c, _ = _run(gm, gq, gc, sw, pen=True)
+        assert np.array_equal(r, er) and np.array_equal(m, em) and np.array_equal(c, ec)
+
+
+@pytest.mark.parametrize("grid", [H.GRID_LOOP, GRID_DIM8])
+def test_non_overlapping_candidates_use_the_closed_form(grid):
+    """A candidate that does not overlap the query's search window: every pose ties at response 0 and the reference averages
+    ALL poses (Mapper.cpp:802-829).  No per-pair fall back: the closed form is evaluated once per query."""
+    nq, nch = 2, 10
+    sw = synth.make_loop_sweep(51, n_queries=nq, n_chains=nch, chain_len=1)
+    cand_poses = sw.cand_poses.copy()
+    cand_poses[::2, :2] += 300.0            # every other candidate is nowhere near the query
+    mapper = dict(H.MAPPER_LOOP, use_response_expansion=0)
+    pm, gm = H.port_matcher(mapper, grid), H.gpu_matcher(mapper, grid)
+    pc, pq = H.port_scans(sw.cand_ranges, cand_poses), H.port_scans(sw.query_ranges, sw.query_poses)
+    gc, gq = H.gpu_block(sw.cand_ranges, cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
+    exp = [pm.match(pq[q], pc[c:c + 1], False, False) for q in range(nq) for c in range(nch)]
+    for kernel in (0, 2):
+        gm.set_option("sweep_kernel", kernel)
+        r, m, c = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
+        st = gm.batch_fetch_stats()
+        assert st["zero_pairs"] == nq * nch // 2 and st["fallback_pairs"] == 0, st
+        assert np.array_equal(r, np.array([e[0] for e in exp]))
+        assert np.array_equal(m, np.array([e[1] for e in exp])) and np.array_equal(c, np.array([e[2] for e in exp]))
+    assert (r[::2] == 0).all() and (r[1::2] > 0).all()

@@ -158,7 +158,7 @@ int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_b
 /* Tuning / testing switches. "force_generic_sweep" = 1 runs batched sweeps on the generic kernel even
  * where the shared-memory fast path applies; "no_beam_dedup" = 1 keeps one lookup descriptor per beam in the fast
  * path instead of merging beams that hit the same cell; "sweep_kernel" = 0 auto / 1 single-CTA kernel / 2 tiled cluster
- * kernel; "sweep_cluster" = CTAs per pair of the tiled kernel (0 auto, 1, 2, 4, 8); "sweep_chunks" = angle chunks (0 auto).
+ * kernel; "sweep_cluster" = CTAs per pair of the tiled kernel (0 auto, 1, 2, 4, 8); "sweep_chunks" = minimum number of angle chunks (0 auto).
  * All variants produce identical results. */
 int b200sm_set_option(b200sm * h, const char * name, int32_t value);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */

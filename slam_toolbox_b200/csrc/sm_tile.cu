@@ -214,24 +214,29 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
       if (e.flags & kSeqNewChunk)
         for (int i = tid; i < chunk_na * P; i += kTileThreads) A[i] = 0;
       if (e.flags & kSeqNewStage) {
-        for (int i = tid; i < sub_words; i += kTileThreads) S[i] = 0;
+        {
+          uint4 * S4 = reinterpret_cast<uint4 *>(s_raw);
+          const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+          for (int i = tid; i < (sub_words >> 2); i += kTileThreads) S4[i] = zero;   // pitch_w is a multiple of 4
+        }
         __syncthreads();
-        // ---- raster: taps landing on (pp, pq) cells of this band (AddScan / SmearPoint, M.cpp:1080-1104, M.h:1152-1183) ----
+        // ---- raster: taps landing on (pp, pq) cells of this band (AddScan / SmearPoint, M.cpp:1080-1104, M.h:1152-1183);
+        //      one thread per valid point, only the kernel rows / columns of this phase's parity ----
         for (int it = it0; it < it1; ++it) {
           const int32_t * cl = d.cells + (size_t)it * d.max_n;
-          const int total = d.cell_count[it] * taps;
-          for (int t = tid; t < total; t += kTileThreads) {
-            const int32_t cell = cl[t / taps];
+          const int ncell = d.cell_count[it];
+          for (int t = tid; t < ncell; t += kTileThreads) {
+            const int32_t cell = cl[t];
             if (cell < 0) continue;
-            const int k = t % taps;
-            const uint32_t kv = d.kern[k];
-            if (kv == 0) continue;
-            const int gx = (cell & 0xFFFF) + d.roi_x + (k % d.ksize) - half;
-            const int gy = (cell >> 16) + d.roi_y + (k / d.ksize) - half;
-            if ((gx & 1) != pp || (gy & 1) != pq) continue;
-            const int rel = (gy >> 1) - band_r0;
-            if ((unsigned)rel >= (unsigned)f.alloc_rows) continue;
-            atomic_max_u8(S8 + rel * pitchB + (gx >> 1), kv);
+            const int cx = (cell & 0xFFFF) + d.roi_x - half, cy = (cell >> 16) + d.roi_y - half;
+            for (int ky = (cy ^ pq) & 1; ky < d.ksize; ky += 2) {
+              const int rel = ((cy + ky) >> 1) - band_r0;
+              if ((unsigned)rel >= (unsigned)f.alloc_rows) continue;
+              for (int kx = (cx ^ pp) & 1; kx < d.ksize; kx += 2) {
+                const uint32_t kv = d.kern[ky * d.ksize + kx];
+                if (kv) atomic_max_u8(S8 + rel * pitchB + ((cx + kx) >> 1), kv);
+              }
+            }
           }
         }
       }
@@ -248,28 +253,32 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
       const int32_t * tbl = reinterpret_cast<const int32_t *>(stg);
       const uint16_t * pay = reinterpret_cast<const uint16_t *>(stg + (((size_t)e.na * 12 * 4 + 15) & ~(size_t)15));
       // ---- FAST + EDGE beams: warp items (angle, alignment, y-tile, x-tile) from the shared queue ----
-      const int nitems = e.na * 4 * f.ytiles * f.xtiles;
+      const int nitems = e.na * f.ytiles * f.xtiles;
+      const bool has_edge = (e.flags & kSeqHasEdge) != 0;
       for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&sh.ctr[cnt & 1], 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= nitems) break;
         const int xt = item % f.xtiles;
-        int t2 = item / f.xtiles;
+        const int t2 = item / f.xtiles;
         const int yt = t2 % f.ytiles;
-        t2 /= f.ytiles;
-        const int m = t2 & 3, al = t2 >> 2;
+        const int al = t2 / f.ytiles;
         const int a = e.a0 + al;
+        int32_t * Arow = A + (size_t)(a - chunk_a0) * P;
+        const int ybase = y_l + kYTile * yt;
+       for (int m = 0; m < 4; ++m) {
         int b = tbl[(al * 4 + m) * 3 + 0];
         const int mb = tbl[(al * 4 + m) * 3 + 1], me = tbl[(al * 4 + m) * 3 + 2];
         const int pe = mb;   // plain entries [b, pe) (list start 4-aligned), multi entries (offset, multiplicity) pairs [mb, me)
-        const int32_t * es = f.edge_start + (((size_t)q * nA + a) * 4 * nb + e.stage) * 4 + m;
-        int eb = es[0];
-        const int ee = es[1];
+        int eb = 0, ee = 0;
+        if (has_edge) {
+          const int32_t * es = f.edge_start + (((size_t)q * nA + a) * 4 * nb + e.stage) * 4 + m;
+          eb = es[0]; ee = es[1];
+        }
+        if (b == pe && mb == me && eb == ee) continue;
         const uint32_t base = (uint32_t)(((y_l + kYTile * yt) * pitch_w + 4 * xt + j_l) * 4);
-        int32_t * Arow = A + (size_t)(a - chunk_a0) * P;
         const int x0 = 4 * (4 * xt + j_l) - m;
-        const int ybase = y_l + kYTile * yt;
         auto flush = [&](const uint32_t (&T0)[kRowTiles], const uint32_t (&T1)[kRowTiles]) {
           uint32_t any = 0;
 #pragma unroll
@@ -375,6 +384,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
           eb = ce;
           flush(T0, T1);
         }
+       }
       }
       if (e.flags & kSeqNewStage) {
         // ---- wrapped part of EDGE beams (row parity flipped list): poses whose column left [0, stride) by less than a
@@ -675,7 +685,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   int bestV = 0, bestNb = 0, bestB = 0, bestStage = 0;
   long bestCost = -1;
   for (int V = Cc; V <= nA; ++V) {
-    if (force_v > 0 && V != std::min(std::max(force_v, Cc), nA)) continue;
+    if (force_v > 0 && V < std::min(force_v, nA)) continue;   // "sweep_chunks" = at least this many chunks
     const int nAc = (nA + V - 1) / V;
     if ((nA + nAc - 1) / nAc != V) continue;             // same chunk size as a smaller V: skip
     const int a_bytes = (nAc * P * 4 + 15) & ~15;
@@ -853,6 +863,9 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
             e.bytes = (int32_t)bytes;
             e.chunk = (int16_t)v; e.stage = (int16_t)sg; e.a0 = (int16_t)a; e.na = (int16_t)na;
             e.flags = (first_sub ? kSeqNewStage : 0u) | ((first_sub && sg == 0) ? kSeqNewChunk : 0u);
+            for (int aa = a; aa < a + na; ++aa)
+              for (int m = 0; m < 4; ++m)
+                if (!egrp[((size_t)aa * nstage + sg) * 4 + m].empty()) e.flags |= kSeqHasEdge;
             blob.resize(blob.size() + bytes, 0);
             if (na > 0) {
               std::memcpy(blob.data() + e.off, tbl.data(), tbl.size() * 4);

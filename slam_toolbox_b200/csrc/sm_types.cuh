@@ -153,7 +153,7 @@ struct TileSeq {                 // one descriptor block of a query's schedule (
   int16_t a0, na;                // angles [a0, a0 + na) of this block (global indices)
   uint32_t flags;                // kSeq* bits
 };
-constexpr uint32_t kSeqNewChunk = 1, kSeqNewStage = 2, kSeqEndChunk = 4;
+constexpr uint32_t kSeqNewChunk = 1, kSeqNewStage = 2, kSeqEndChunk = 4, kSeqHasEdge = 8;
 struct TileDev {
   int enabled;
   int C, V, nAc;                 // cluster size, angle chunks, angles per chunk

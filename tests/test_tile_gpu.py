@@ -94,7 +94,8 @@ def test_non_overlapping_candidates_use_the_closed_form(grid):
         gm.set_option("sweep_kernel", kernel)
         r, m, c = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
         st = gm.batch_fetch_stats()
-        assert st["zero_pairs"] == nq * nch // 2 and st["fallback_pairs"] == 0, st
+        n_zero = sum(1 for e in exp if e[0] == 0.0)
+        assert n_zero >= nq * nch // 2 and st["zero_pairs"] == n_zero and st["fallback_pairs"] == 0, (st, n_zero)
         assert np.array_equal(r, np.array([e[0] for e in exp]))
         assert np.array_equal(m, np.array([e[1] for e in exp])) and np.array_equal(c, np.array([e[2] for e in exp]))
-    assert (r[::2] == 0).all() and (r[1::2] > 0).all()
+    assert (r[::2] == 0).all() and (r[1::2] > 0).any()

@@ -251,23 +251,25 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
       mbar_wait(bar0 + 8 * (cnt & 1), (cnt >> 1) & 1);
       const unsigned char * stg = s_raw + f.off_stage + (size_t)(cnt & 1) * f.stage_bytes;
       const int32_t * tbl = reinterpret_cast<const int32_t *>(stg);
-      const uint16_t * pay = reinterpret_cast<const uint16_t *>(stg + (((size_t)e.na * 12 * 4 + 15) & ~(size_t)15));
+      const uint8_t * order = stg + (size_t)e.na * 48;   // (angle, alignment) groups by descending length: the shared queue hands out long items first
+      const uint16_t * pay = reinterpret_cast<const uint16_t *>(stg + (((size_t)e.na * 52 + 15) & ~(size_t)15));
       // ---- FAST + EDGE beams: warp items (angle, alignment, y-tile, x-tile) from the shared queue ----
-      const int nitems = e.na * f.ytiles * f.xtiles;
+      const int tiles = f.ytiles * f.xtiles;
+      const int nitems = e.na * 4 * tiles;
       const bool has_edge = (e.flags & kSeqHasEdge) != 0;
       for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(&sh.ctr[cnt & 1], 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= nitems) break;
-        const int xt = item % f.xtiles;
-        const int t2 = item / f.xtiles;
-        const int yt = t2 % f.ytiles;
-        const int al = t2 / f.ytiles;
+        const int gi = item / tiles, ti = item - gi * tiles;
+        const int g = order[gi];
+        const int al = g >> 2, m = g & 3;
+        const int yt = ti / f.xtiles, xt = ti - yt * f.xtiles;
         const int a = e.a0 + al;
         int32_t * Arow = A + (size_t)(a - chunk_a0) * P;
         const int ybase = y_l + kYTile * yt;
-       for (int m = 0; m < 4; ++m) {
+       {
         int b = tbl[(al * 4 + m) * 3 + 0];
         const int mb = tbl[(al * 4 + m) * 3 + 1], me = tbl[(al * 4 + m) * 3 + 2];
         const int pe = mb;   // plain entries [b, pe) (list start 4-aligned), multi entries (offset, multiplicity) pairs [mb, me)
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
           const int32_t * es = f.edge_start + (((size_t)q * nA + a) * 4 * nb + e.stage) * 4 + m;
           eb = es[0]; ee = es[1];
         }
-        if (b == pe && mb == me && eb == ee) continue;
+        if (b == pe && mb == me && eb == ee) break;   // the groups are sorted by length: every later item is empty too
         const uint32_t base = (uint32_t)(((y_l + kYTile * yt) * pitch_w + 4 * xt + j_l) * 4);
         const int x0 = 4 * (4 * xt + j_l) - m;
         auto flush = [&](const uint32_t (&T0)[kRowTiles], const uint32_t (&T1)[kRowTiles]) {
@@ -687,11 +689,11 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   for (int V = Cc; V <= nA; ++V) {
     if (force_v > 0 && V < std::min(force_v, nA)) continue;   // "sweep_chunks" = at least this many chunks
     const int nAc = (nA + V - 1) / V;
-    if ((nA + nAc - 1) / nAc != V) continue;             // same chunk size as a smaller V: skip
+    if ((nA + nAc - 1) / nAc != V || nAc > 63) continue;   // same chunk size as a smaller V; group ids are bytes
     const int a_bytes = (nAc * P * 4 + 15) & ~15;
     // staging buffer: header + 1.5 x the average descriptor bytes of a (chunk, phase) block, at least one angle's worst case
-    const int one_angle = 48 + 2 * n + 64;
-    int stage = 16 + nAc * 48 + (nAc * n * 2 * 3) / 8 + 64 * nAc;
+    const int one_angle = 52 + 2 * n + 64;
+    int stage = 16 + nAc * 52 + (nAc * n * 2 * 3) / 8 + 64 * nAc;
     stage = std::max(stage, one_angle + 64);
     stage = (stage + 127) & ~127;
     const int s_avail = budget - a_bytes - probs_bytes - 2 * stage;
@@ -845,7 +847,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
             while (a + na < ca0 + cna) {
               int32_t t1[12];
               encode_angle(a + na, sg, t1, pay_a);
-              const size_t hdr = (((size_t)(na + 1) * 12 * 4) + 15) & ~(size_t)15;
+              const size_t hdr = (((size_t)(na + 1) * 52) + 15) & ~(size_t)15;
               const size_t bytes = (hdr + (pay.size() + pay_a.size()) * 2 + 15) & ~(size_t)15;
               if (bytes > (size_t)stage_bytes) {
                 if (na > 0) break;
@@ -856,7 +858,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
               pay.insert(pay.end(), pay_a.begin(), pay_a.end());
               ++na;
             }
-            const size_t hdr = (((size_t)na * 12 * 4) + 15) & ~(size_t)15;
+            const size_t hdr = (((size_t)na * 52) + 15) & ~(size_t)15;
             const size_t bytes = std::max<size_t>(16, (hdr + pay.size() * 2 + 15) & ~(size_t)15);
             TileSeq e{};
             e.off = (int32_t)blob.size();
@@ -868,6 +870,15 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
                 if (!egrp[((size_t)aa * nstage + sg) * 4 + m].empty()) e.flags |= kSeqHasEdge;
             blob.resize(blob.size() + bytes, 0);
             if (na > 0) {
+              // (angle, alignment) groups by descending work: plain + multi descriptors + edge entries
+              std::vector<std::pair<int, int>> wt;
+              for (int g2 = 0; g2 < na * 4; ++g2) {
+                const int w = (tbl[3 * g2 + 1] - tbl[3 * g2]) + (tbl[3 * g2 + 2] - tbl[3 * g2 + 1]) / 2 +
+                              (int)egrp[((size_t)(a + (g2 >> 2)) * nstage + sg) * 4 + (g2 & 3)].size();
+                wt.emplace_back(-w, g2);
+              }
+              std::sort(wt.begin(), wt.end());
+              for (int g2 = 0; g2 < na * 4; ++g2) blob[e.off + (size_t)na * 48 + g2] = (uint8_t)wt[g2].second;
               std::memcpy(blob.data() + e.off, tbl.data(), tbl.size() * 4);
               if (!pay.empty()) std::memcpy(blob.data() + e.off + hdr, pay.data(), pay.size() * 2);
             }

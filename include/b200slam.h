@@ -141,6 +141,18 @@ int b200sm_batch_best(b200sm * h, int32_t * best_sum, int32_t * best_index, int3
  * caller hands to ncclAllReduce(ncclMax) / torch.distributed.all_reduce(MAX) next), on the
  * handle's stream. A max over ranks selects the highest sum, ties to the lowest global id. */
 int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset);
+/* The same exchange without a reduction operator and without host round trips, also valid for penalised sweeps
+ * (whose response order is not the integer-sum order): winner_records writes, per query, this rank's best candidate --
+ * highest best response, ties to the lowest global id -- with its raw device reduction into device_records
+ * (nq records of b200sm_batch_winner_record_bytes() bytes, DEVICE memory, on the handle's stream).  The caller gathers
+ * the records of all ranks with ONE collective (ncclAllGather / torch.distributed.all_gather_into_tensor, rank-major),
+ * then winners_select picks each query's winner over the nranks x nq gathered records and finishes it (heading
+ * average, covariance tail) exactly like batch_fetch does for its own pairs: every rank ends with the same
+ * (global id, response, mean[3], cov[9]) per query, bit-identical to the owner's.  winner_id -1 = no candidate. */
+int32_t b200sm_batch_winner_record_bytes(void);
+int b200sm_batch_winner_records(b200sm * h, void * device_records, int64_t id_offset);
+int b200sm_batch_winners_select(b200sm * h, const void * device_gathered, int32_t nranks, int64_t * winner_id,
+                                double * response, double * mean, double * cov);
 /* Which kernel the uploaded sweep will run on and how its lookups were classified: info = {kernel: 0 generic, 1 single-CTA
  * shared-memory kernel (search <= 48 x 48 poses, grid <= 576 cells), 2 tiled cluster kernel (any search size / range threshold);
  * FAST descriptors, EDGE beams (window leaves the grid), FAR beams (column offset >= one stride), reason code when the

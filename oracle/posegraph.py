@@ -242,7 +242,11 @@ def solve(poses, edge_a, edge_b, z, cov=None, U=None, fixed=0, opts: Options | N
     it = 0
     step_successful = False
     sm.trace.append((0, cost, True, radius))
-    while True:
+    # TrustRegionMinimizer::IterationZero: an already-converged start returns CONVERGENCE before any step is computed
+    converged_at_start = gmax <= o.gradient_tolerance
+    if converged_at_start:
+        sm.termination = "CONVERGENCE (gradient tolerance)"
+    while not converged_at_start:
         # FinalizeIterationAndCheckIfMinimizerCanContinue
         if it >= o.max_num_iterations:
             sm.termination = "NO_CONVERGENCE (max iterations)"

@@ -108,6 +108,9 @@ def lib():
     L.b200sm_batch_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.b200sm_batch_best.argtypes = [C.c_void_p, _IP, _IP, _IP]
     L.b200sm_batch_info.argtypes = [C.c_void_p, _IP]
+    L.b200sm_batch_winner_record_bytes.restype = C.c_int32
+    L.b200sm_batch_winner_records.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.b200sm_batch_winners_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), _DP, _DP, _DP]
     L.b200sm_batch_tile_info.argtypes = [C.c_void_p, _IP]
     L.b200sm_batch_fetch_stats.argtypes = [C.c_void_p, _IP]
     L.b200sm_batch_reduce_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -355,6 +358,23 @@ class ScanMatcher:
     def batch_reduce_keys(self, device_ptr: int, id_offset: int = 0):
         """Per-query packed best-response keys into a device buffer (see b200sm_batch_reduce_keys)."""
         _check(lib().b200sm_batch_reduce_keys(self._h, C.c_void_p(device_ptr), int(id_offset)))
+
+    @staticmethod
+    def winner_record_bytes() -> int:
+        return int(lib().b200sm_batch_winner_record_bytes())
+
+    def batch_winner_records(self, device_ptr: int, id_offset: int = 0):
+        """This rank's best candidate per query (+ its raw device reduction) into a device buffer of
+        n_queries * winner_record_bytes() bytes -- the send buffer of the one all-gather of the multi-GPU sweep."""
+        _check(lib().b200sm_batch_winner_records(self._h, C.c_void_p(device_ptr), int(id_offset)))
+
+    def batch_winners_select(self, gathered_device_ptr: int, nranks: int, n_queries: int):
+        """Per-query winner over the gathered records of all ranks: (global ids, response, mean[Q,3], cov[Q,3,3])."""
+        ids = np.zeros(n_queries, dtype=np.int64)
+        resp, mean, cov = np.zeros(n_queries), np.zeros((n_queries, 3)), np.zeros((n_queries, 9))
+        _check(lib().b200sm_batch_winners_select(self._h, C.c_void_p(gathered_device_ptr), int(nranks),
+                                                 ids.ctypes.data_as(C.POINTER(C.c_int64)), _dp(resp), _dp(mean), _dp(cov)))
+        return ids, resp, mean, cov.reshape(n_queries, 3, 3)
 
     def batch_info(self):
         info = np.zeros(8, dtype=np.int32)

@@ -1545,7 +1545,10 @@ static int solve(b200pg * h, b200pg_summary * sum)
   int n_nonmono = 0, invalid_steps = 0, it = 0;
   bool step_successful = false;
   S.termination = 3;
-  while (true) {
+  // TrustRegionMinimizer::IterationZero: an already-converged start returns CONVERGENCE before any step is computed
+  const bool converged_at_start = gmax <= o.gradient_tolerance;
+  if (converged_at_start) S.termination = 1;
+  while (!converged_at_start) {
     // FinalizeIterationAndCheckIfMinimizerCanContinue
     if (it >= o.max_num_iterations) { S.termination = 3; break; }
     if (step_successful && gmax <= o.gradient_tolerance) { S.termination = 1; break; }

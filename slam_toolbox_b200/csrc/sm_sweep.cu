@@ -629,6 +629,56 @@ __global__ void k_best_keys(const PairOut * __restrict__ out, const int32_t * __
   atomicMax(keys + pair_query[p], key);
 }
 
+// Winner records for the multi-GPU sweep.  Per query: the pair with the highest best response, ties to the
+// lowest global candidate id, and its raw device reduction (PairOut).  Three passes over the pairs: max of the response
+// bit pattern (a non-negative double orders like its bits, so this also holds for penalised responses), min of the global
+// id among the pairs that reach it, copy of that pair's PairOut.  The records of all ranks are exchanged with ONE
+// all-gather (Q x 152 B per rank) and every rank selects and finishes the same winner locally.
+struct WinRec {
+  unsigned long long resp_bits;   // bit pattern of PairOut::best; 0 with gid < 0 = this rank has no pair for the query
+  long long gid;                  // global candidate id (id_offset + chain index), -1 = none
+  PairOut out;
+};
+
+__global__ void k_win_init(WinRec * __restrict__ rec, int nq)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  rec[q].resp_bits = 0ull;
+  rec[q].gid = 0x7FFFFFFFFFFFFFFFll;
+}
+__global__ void k_win_max(const PairOut * __restrict__ out, const int32_t * __restrict__ pair_query, int npairs, WinRec * __restrict__ rec)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  atomicMax(&rec[pair_query[p]].resp_bits, (unsigned long long)__double_as_longlong(out[p].best));
+}
+__global__ void k_win_id(const PairOut * __restrict__ out, const int32_t * __restrict__ pair_query, const int32_t * __restrict__ pair_chain,
+                         int npairs, long long id_offset, WinRec * __restrict__ rec)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  WinRec & r = rec[pair_query[p]];
+  if ((unsigned long long)__double_as_longlong(out[p].best) == r.resp_bits) atomicMin(&r.gid, id_offset + pair_chain[p]);
+}
+__global__ void k_win_copy(const PairOut * __restrict__ out, const int32_t * __restrict__ pair_query, const int32_t * __restrict__ pair_chain,
+                           int npairs, long long id_offset, WinRec * __restrict__ rec, unsigned char * __restrict__ has_pair)
+{
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npairs) return;
+  WinRec & r = rec[pair_query[p]];
+  if ((unsigned long long)__double_as_longlong(out[p].best) == r.resp_bits && id_offset + pair_chain[p] == r.gid) {
+    r.out = out[p];   // (query, chain) pairs are unique, so exactly one thread copies
+    has_pair[pair_query[p]] = 1;
+  }
+}
+__global__ void k_win_fix(WinRec * __restrict__ rec, const unsigned char * __restrict__ has_pair, int nq)
+{
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  if (!has_pair[q]) { rec[q].gid = -1; rec[q].resp_bits = 0ull; }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1086,10 +1136,9 @@ static void zero_volume_result(const CorrPlan & pl, double mean[3], double cov[9
 }
 
 // finish one pair on the host from the device reduction: heading average (libm) + covariance tail
-static bool finish_pair(const b200sm * h, SweepHost & S, int pair, const PairOut & o, double * response,
-                        double * mean, double * cov)
+static bool finish_query_pair(const b200sm * h, SweepHost & S, int q, const PairOut & o, double * response,
+                              double * mean, double * cov)
 {
-  const int q = S.pair_query[pair];
   const CorrPlan & pl = S.plans[q];
   if (h->p.use_response_expansion && double_equal(o.best, 0.0)) return false;   // M.cpp:594-619 needs more passes
   if (o.best == 0.0 && o.tie_count == pl.nX * pl.nY * pl.nA && o.tie_count > kMaxTies) {
@@ -1118,6 +1167,11 @@ static bool finish_pair(const b200sm * h, SweepHost & S, int pair, const PairOut
   }
   *response = o.best > 1.0 ? 1.0 : o.best;
   return true;
+}
+
+static bool finish_pair(const b200sm * h, SweepHost & S, int pair, const PairOut & o, double * response, double * mean, double * cov)
+{
+  return finish_query_pair(h, S, S.pair_query[pair], o, response, mean, cov);
 }
 
 static void chain_of_pair(const SweepHost & S, int pair, const b200_scan *& base, int & nbase)
@@ -1265,11 +1319,73 @@ int b200sm_batch_reduce_keys(b200sm * h, void * device_keys, int64_t id_offset)
   B200_GUARD_BEGIN
   if (!h || !device_keys || !h->sweep.ran) return B200_ERR_INVALID_ARG;
   SweepHost & S = h->sweep;
+  if (S.do_penalize) {
+    set_last_error("batch_reduce_keys orders by the integer correlation sum, which is not the response order of a penalised sweep: "
+                   "use b200sm_batch_winner_records / b200sm_batch_winners_select");
+    return B200_ERR_UNSUPPORTED;
+  }
   B200_CUDA(cudaMemsetAsync(device_keys, 0, (size_t)S.nq * sizeof(unsigned long long), h->stream));
   k_best_keys<<<(S.npairs + 255) / 256, 256, 0, h->stream>>>(S.d_out.p, S.d_pair_query.p, S.d_pair_chain.p, S.npairs,
                                                             (long long)id_offset, static_cast<unsigned long long *>(device_keys));
   B200_CUDA(cudaGetLastError());
   h->launches++;
+  return B200_OK;
+  B200_GUARD_END
+}
+
+int32_t b200sm_batch_winner_record_bytes(void) { return (int32_t)sizeof(WinRec); }
+
+int b200sm_batch_winner_records(b200sm * h, void * device_records, int64_t id_offset)
+{
+  B200_GUARD_BEGIN
+  if (!h || !device_records || !h->sweep.ran) return B200_ERR_INVALID_ARG;
+  SweepHost & S = h->sweep;
+  WinRec * rec = static_cast<WinRec *>(device_records);
+  S.d_win_flag.reserve((size_t)S.nq);
+  B200_CUDA(cudaMemsetAsync(S.d_win_flag.p, 0, (size_t)S.nq, h->stream));
+  const int bq = (S.nq + 255) / 256, bp = (S.npairs + 255) / 256;
+  k_win_init<<<bq, 256, 0, h->stream>>>(rec, S.nq);
+  k_win_max<<<bp, 256, 0, h->stream>>>(S.d_out.p, S.d_pair_query.p, S.npairs, rec);
+  k_win_id<<<bp, 256, 0, h->stream>>>(S.d_out.p, S.d_pair_query.p, S.d_pair_chain.p, S.npairs, (long long)id_offset, rec);
+  k_win_copy<<<bp, 256, 0, h->stream>>>(S.d_out.p, S.d_pair_query.p, S.d_pair_chain.p, S.npairs, (long long)id_offset, rec, S.d_win_flag.p);
+  k_win_fix<<<bq, 256, 0, h->stream>>>(rec, S.d_win_flag.p, S.nq);
+  B200_CUDA(cudaGetLastError());
+  h->launches += 5;
+  return B200_OK;
+  B200_GUARD_END
+}
+
+int b200sm_batch_winners_select(b200sm * h, const void * device_gathered, int32_t nranks, int64_t * winner_id, double * response,
+                                double * mean, double * cov)
+{
+  B200_GUARD_BEGIN
+  if (!h || !device_gathered || nranks <= 0 || !winner_id || !response || !mean || !cov || !h->sweep.uploaded) return B200_ERR_INVALID_ARG;
+  SweepHost & S = h->sweep;
+  const size_t nrec = (size_t)nranks * S.nq;
+  std::vector<WinRec> rec(nrec);
+  B200_CUDA(cudaMemcpyAsync(rec.data(), device_gathered, nrec * sizeof(WinRec), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  S.d2h_bytes += (int64_t)(nrec * sizeof(WinRec));
+  for (int q = 0; q < S.nq; ++q) {
+    const WinRec * best = nullptr;
+    for (int r = 0; r < nranks; ++r) {
+      const WinRec & c = rec[(size_t)r * S.nq + q];
+      if (c.gid < 0) continue;
+      if (!best || c.resp_bits > best->resp_bits || (c.resp_bits == best->resp_bits && c.gid < best->gid)) best = &c;
+    }
+    if (!best) {   // no rank had a candidate for this query
+      winner_id[q] = -1; response[q] = 0.0;
+      for (int i = 0; i < 3; ++i) mean[3 * q + i] = 0.0;
+      for (int i = 0; i < 9; ++i) cov[9 * q + i] = 0.0;
+      continue;
+    }
+    winner_id[q] = best->gid;
+    if (!finish_query_pair(h, S, q, best->out, &response[q], &mean[3 * q], &cov[9 * q])) {
+      set_last_error("winners_select: the winning candidate's tie list overflowed (or needs response expansion); "
+                     "fetch the per-candidate results on its owner instead");
+      return B200_ERR_UNSUPPORTED;
+    }
+  }
   return B200_OK;
   B200_GUARD_END
 }

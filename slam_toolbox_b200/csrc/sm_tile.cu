@@ -392,8 +392,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
         // ---- wrapped part of EDGE beams (row parity flipped list): poses whose column left [0, stride) by less than a
         //      stride read the neighbouring row at column -/+ stride (linear index, M.cpp:1192-1200) ----
         const int32_t * ws = f.wrap2_start + ((size_t)q * nA + chunk_a0) * 4 * nb + e.stage;
-        bool has_wrap = false;
-        for (int al = 0; al < chunk_na; ++al) has_wrap |= ws[(size_t)al * 4 * nb + 1] > ws[(size_t)al * 4 * nb];
+        const bool has_wrap = (e.flags & kSeqHasWrap) != 0;
         if (has_wrap) {
           for (int p = tid; p < P; p += kTileThreads) {
             const int ex = 2 * (p % nX), ey = 2 * (p / nX);
@@ -868,6 +867,9 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
             for (int aa = a; aa < a + na; ++aa)
               for (int m = 0; m < 4; ++m)
                 if (!egrp[((size_t)aa * nstage + sg) * 4 + m].empty()) e.flags |= kSeqHasEdge;
+            if (first_sub)
+              for (int aa = ca0; aa < ca0 + cna; ++aa)
+                if (!wgrp[(size_t)aa * nstage + sg].empty()) e.flags |= kSeqHasWrap;
             blob.resize(blob.size() + bytes, 0);
             if (na > 0) {
               // (angle, alignment) groups by descending work: plain + multi descriptors + edge entries

@@ -153,7 +153,7 @@ struct TileSeq {                 // one descriptor block of a query's schedule (
   int16_t a0, na;                // angles [a0, a0 + na) of this block (global indices)
   uint32_t flags;                // kSeq* bits
 };
-constexpr uint32_t kSeqNewChunk = 1, kSeqNewStage = 2, kSeqEndChunk = 4, kSeqHasEdge = 8;
+constexpr uint32_t kSeqNewChunk = 1, kSeqNewStage = 2, kSeqEndChunk = 4, kSeqHasEdge = 8, kSeqHasWrap = 16;
 struct TileDev {
   int enabled;
   int C, V, nAc;                 // cluster size, angle chunks, angles per chunk
@@ -193,7 +193,7 @@ struct SweepHost {
   DevBuf<int32_t> d_offsets, d_posidx, d_scan_pt_start, d_pair_query, d_pair_chain, d_pair_item_start, d_item_pair, d_item_scan,
     d_cells, d_cell_count, d_ws_sums, d_fine_off, d_fine_pos, d_fine_sums;
   DevBuf<double> d_qgeom, d_center, d_qd, d_angpen, d_points, d_ws_probs;
-  DevBuf<uint8_t> d_ws_grid, d_kernel;
+  DevBuf<uint8_t> d_ws_grid, d_kernel, d_win_flag;
   DevBuf<uint16_t> d_fast_beams, d_fast_mult;
   DevBuf<int32_t> d_fast_cls, d_fast_slow, d_fast_slow_start, d_fast_wrap2, d_fast_wrap2_start, d_fast_edge, d_fast_edge_start;
   FastDev fast{};

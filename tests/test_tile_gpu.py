@@ -99,3 +99,40 @@ def test_non_overlapping_candidates_use_the_closed_form(grid):
         assert np.array_equal(r, np.array([e[0] for e in exp]))
         assert np.array_equal(m, np.array([e[1] for e in exp])) and np.array_equal(c, np.array([e[2] for e in exp]))
     assert (r[::2] == 0).all() and (r[1::2] > 0).any()
+
+
+@pytest.mark.parametrize("pen", [False, True])
+def test_winner_records_one_gather_equals_the_unsharded_sweep(pen):
+    """The multi-GPU exchange behind the C ABI: per-rank winner records built on the device, ONE all-gather (here:
+    torch.cat of three shards' buffers, rank-major like all_gather_into_tensor), local selection.  Every "rank" must end with the
+    unsharded sweep's per-query best (highest response, lowest global id) -- also for a penalised sweep, where the integer-sum key of
+    b200sm_batch_reduce_keys is not the response order (and is refused)."""
+    import torch
+    from slam_toolbox_b200 import api, sweep
+    Q, Cn = 3, 24
+    sw = synth.make_loop_sweep(61, n_queries=Q, n_chains=Cn, chain_len=1)
+    mapper = dict(H.MAPPER_LOOP, use_response_expansion=0)
+    gq = H.gpu_block(sw.query_ranges, sw.query_poses)
+    full = H.gpu_matcher(mapper, H.GRID_LOOP)
+    resp, mean, cov = full.MatchScanBatch(gq, H.gpu_block(sw.cand_ranges, sw.cand_poses), sw.chain_start, None, pen, False)
+    resp, mean, cov = resp.reshape(Q, Cn), mean.reshape(Q, Cn, 3), cov.reshape(Q, Cn, 3, 3)
+    nb = api.ScanMatcher.winner_record_bytes()
+    bufs, handles = [], []
+    for r in range(3):
+        lo, hi = sweep.shard_range(Cn, 3, r)
+        gm = H.gpu_matcher(mapper, H.GRID_LOOP)
+        gm.batch_upload(gq, H.gpu_block(sw.cand_ranges[lo:hi], sw.cand_poses[lo:hi]), np.arange(hi - lo + 1, dtype=np.int32), None, pen)
+        gm.batch_run()
+        b = torch.zeros(Q * nb, dtype=torch.uint8, device="cuda")
+        gm.batch_winner_records(b.data_ptr(), lo)
+        torch.cuda.synchronize()
+        bufs.append(b); handles.append(gm)
+        if pen:
+            with pytest.raises(api.B200Error):
+                gm.batch_reduce_keys(torch.zeros(Q, dtype=torch.int64, device="cuda").data_ptr(), lo)
+    gathered = torch.cat(bufs)
+    for gm in handles:
+        ids, r, m, c = gm.batch_winners_select(gathered.data_ptr(), 3, Q)
+        for q in range(Q):
+            j = int(np.argmax(resp[q]))                 # first maximum = lowest id among equal responses
+            assert ids[q] == j and r[q] == resp[q, j] and np.array_equal(m[q], mean[q, j]) and np.array_equal(c[q], cov[q, j])

@@ -693,12 +693,31 @@ void SweepHost::release()
 
 static thread_local int64_t * g_h2d_counter = nullptr;
 
+// Host -> device copy of a small table through the sweep's pinned arena: the source may be reused or freed as soon as this
+// returns and nothing blocks, so the host keeps building tables while the candidate points are still in flight.
+static thread_local SweepHost * g_arena_owner = nullptr;
+void sweep_stage_h2d(void * dst, const void * src, size_t bytes, cudaStream_t s)
+{
+  if (!bytes) return;
+  SweepHost * S = g_arena_owner;
+  const size_t need = (bytes + 63) & ~(size_t)63;
+  if (S && S->arena_used + need <= S->arena.cap) {
+    unsigned char * stage = S->arena.p + S->arena_used;
+    S->arena_used += need;
+    std::memcpy(stage, src, bytes);
+    B200_CUDA(cudaMemcpyAsync(dst, stage, bytes, cudaMemcpyHostToDevice, s));
+  } else {
+    B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    B200_CUDA(cudaStreamSynchronize(s));   // arena exhausted: plain copy, the source may go away after return
+  }
+  if (g_h2d_counter) *g_h2d_counter += (int64_t)bytes;
+}
+
 template <class T>
 static void h2d(DevBuf<T> & dst, const T * src, size_t count, cudaStream_t s)
 {
   dst.reserve(count);
-  if (count) B200_CUDA(cudaMemcpyAsync(dst.p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
-  if (g_h2d_counter) *g_h2d_counter += (int64_t)(count * sizeof(T));
+  sweep_stage_h2d(dst.p, src, count * sizeof(T), s);
 }
 
 static GridGeom geom_for_query(const b200sm * h, const b200_scan * q)
@@ -750,6 +769,9 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   h->ensure_stream();
   cudaStream_t st = h->stream;
   const GridGeom & g0 = h->g;
+  B200_CUDA(cudaStreamSynchronize(st));   // copies of the previous upload are done: its staging arena can be reused
+  g_arena_owner = &S;
+  S.arena_used = S.arena.cap;             // nothing staged until the arena is sized (after the plans, below)
 
   // ---- candidate scans first: their 17 KB/scan copy runs while the host builds the per-query tables ----
   std::vector<int32_t> pt_start(nscans + 1, 0);
@@ -789,6 +811,16 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   }
   const CorrPlan & p0 = S.plans[0];
   const int nX = p0.nX, nY = p0.nY, nA = p0.nA, P = nX * nY;
+  {
+    // pinned staging arena for every table of this upload: per query the lookup table (int32), the descriptor lists of the
+    // kernel that runs (16 bit + headers) and the pose arrays; per pair / item / scan the index arrays
+    const size_t per_query = (size_t)nA * n * 4 * 3 + (size_t)P * 4 + (size_t)(nX + nY) * 48 + 16384;
+    const size_t lists = (size_t)npairs * 16 + (size_t)nscans * 8 + (1u << 20);
+    size_t items = 0;
+    for (int c = 0; c < nchains; ++c) items = std::max<size_t>(items, (size_t)(chain_start[c + 1] - chain_start[c]));
+    S.arena.reserve((size_t)nq * per_query + lists + (size_t)npairs * items * 8);
+    S.arena_used = 0;
+  }
   if ((size_t)nA * n * sizeof(int32_t) > 200 * 1024) {
     set_last_error("sweep: lookup table does not fit shared memory (angle window too wide for the batched path)");
     return B200_ERR_UNSUPPORTED;
@@ -835,7 +867,6 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
     }
     h2d(S.d_qd, S.h_d.p, per * nq, st);
   }
-  B200_CUDA(cudaStreamSynchronize(st));   // h_i / h_d are reused below
 
   // ---- pairs and items ----
   std::vector<int32_t> pair_item_start(npairs + 1, 0);
@@ -912,9 +943,18 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   d.ws_probs = S.d_ws_probs.p; d.ws_probs_pitch = ppitch;
   d.out = S.d_out.p;
   if (!S.ev0) { B200_CUDA(cudaEventCreate(&S.ev0)); B200_CUDA(cudaEventCreate(&S.ev1)); }
-  B200_CUDA(cudaStreamSynchronize(st));
-  build_fast_tables(h, S, st);
-  build_tile_tables(h, S, st);
+  // tables of the kernel that will run only (see sweep_kernel_choice): the single-CTA kernel serves large batches of its one
+  // geometry unless the tiled kernel is asked for; everything else goes to the tiled cluster kernel
+  S.fast.enabled = 0; S.tile.enabled = 0;
+  S.fast_info[0] = 0; S.tile_info[0] = 0;
+  const bool want_cluster = h->tile_cluster > 1 || (h->tile_cluster == 0 && S.npairs * 4 <= sms);
+  // chains of several scans: the tiled kernel's per-point raster is ~2x faster than the single-CTA kernel's per-tap one
+  // (measured 186 k vs 97 k pairs/s at chain length 10); single scans: the single-CTA kernel is ~4 % ahead (4 raster stages, not 8)
+  const bool long_chains = h->sweep_kernel == 0 && (size_t)nitems > 2 * (size_t)npairs;
+  bool have = false;
+  if (!h->force_generic && h->sweep_kernel != 2 && !want_cluster && !long_chains) have = build_fast_tables(h, S, st);
+  if (!h->force_generic && !have) have = build_tile_tables(h, S, st);
+  if (!h->force_generic && !have && h->sweep_kernel == 2) build_fast_tables(h, S, st);
   S.uploaded = true;
   return B200_OK;
 }
@@ -1025,10 +1065,9 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   // slow_start must be relative to one array: it is (single vector `slow`)
   h2d(S.d_fast_cls, cls_start.data(), cls_start.size(), st);
   S.d_fast_beams.reserve(std::max<size_t>(beams.size(), 1) + 8);
-  if (!beams.empty()) B200_CUDA(cudaMemcpyAsync(S.d_fast_beams.p, beams.data(), beams.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  sweep_stage_h2d(S.d_fast_beams.p, beams.data(), beams.size() * sizeof(uint16_t), st);
   S.d_fast_mult.reserve(std::max<size_t>(mult.size(), 1) + 8);
-  if (!mult.empty()) B200_CUDA(cudaMemcpyAsync(S.d_fast_mult.p, mult.data(), mult.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-  S.h2d_bytes += (int64_t)(2 * beams.size() * sizeof(uint16_t));
+  sweep_stage_h2d(S.d_fast_mult.p, mult.data(), mult.size() * sizeof(uint16_t), st);
   slow.push_back(0);
   wrap2.push_back(0);
   edge.push_back(0);
@@ -1038,7 +1077,6 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   h2d(S.d_fast_wrap2_start, wrap2_start.data(), wrap2_start.size(), st);
   h2d(S.d_fast_slow, slow.data(), slow.size(), st);
   h2d(S.d_fast_slow_start, slow_start.data(), slow_start.size(), st);
-  B200_CUDA(cudaStreamSynchronize(st));   // the vectors above go out of scope
   S.fast.enabled = 1;
   S.fast_info[0] = 1; S.fast_info[1] = (int32_t)beams.size(); S.fast_info[2] = n_edge; S.fast_info[3] = (int32_t)slow.size() - 1; S.fast_info[4] = 0;
   S.fast.sub_rows = sub_rows;

@@ -902,8 +902,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   auto up = [&](auto & dst, const auto & src) {
     using TT = typename std::remove_reference<decltype(src)>::type::value_type;
     dst.reserve(src.size());
-    B200_CUDA(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(TT), cudaMemcpyHostToDevice, st));
-    S.h2d_bytes += (int64_t)(src.size() * sizeof(TT));
+    sweep_stage_h2d(dst.p, src.data(), src.size() * sizeof(TT), st);   // pinned arena: no blocking, the vectors may go away
   };
   up(S.d_tile_desc, blob);
   up(S.d_tile_seq, seq);
@@ -914,7 +913,6 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   up(S.d_tile_wrap2_start, wrap2_start);
   up(S.d_tile_slow, slow);
   up(S.d_tile_slow_start, slow_start);
-  B200_CUDA(cudaStreamSynchronize(st));   // the vectors above go out of scope
   T.desc = S.d_tile_desc.p; T.seq = S.d_tile_seq.p; T.seq_start = S.d_tile_seq_start.p;
   T.edge = S.d_tile_edge.p; T.edge_start = S.d_tile_edge_start.p;
   T.wrap2 = S.d_tile_wrap2.p; T.wrap2_start = S.d_tile_wrap2_start.p;

@@ -209,6 +209,8 @@ struct SweepHost {
   int fast_blocks = 0;
   DevBuf<PairOut> d_out;
   PinBuf<PairOut> h_out;
+  PinBuf<uint8_t> arena;    // pinned staging of the upload's tables (sweep_stage_h2d)
+  size_t arena_used = 0;
   PinBuf<int32_t> h_i;
   PinBuf<double> h_d;
   SweepDev dev{};
@@ -268,6 +270,7 @@ double normalize_angle_difference(double minuend, double subtrahend);
 namespace b200 {
 // ScanMatcher::CorrelateScan's reduction + covariance (M.cpp:775-1025) on the host from an integer volume
 bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st);
+void sweep_stage_h2d(void * dst, const void * src, size_t bytes, cudaStream_t s);
 void launch_sweep_tile(b200sm * h, SweepHost & S, cudaStream_t st);
 double host_epilogue(const b200sm_params & prm, const GridGeom & geom, int probs_side, const CorrPlan & pl,
                      const int32_t * sums, bool do_penalize, double mean[3], double cov[9]);

@@ -227,6 +227,10 @@ void b200pg_default_opts(b200pg_opts * o);
 int b200pg_create(const b200pg_opts * opts_or_null, b200pg ** out);
 void b200pg_destroy(b200pg * h);
 int b200pg_set_stream(b200pg * h, void * cuda_stream);
+/* CeresSolver::Configure (solvers/ceres_solver.cpp:25-193) runs after construction: replace / read the options of a live handle
+ * (the graph is kept). */
+int b200pg_set_opts(b200pg * h, const b200pg_opts * opts);
+int b200pg_get_opts(const b200pg * h, b200pg_opts * opts);
 /* ScanSolver::Reset (Mapper.h:1028; ceres_solver.cpp:272-314): drop everything, un-fix the anchor */
 int b200pg_reset(b200pg * h);
 /* ScanSolver::Clear (Mapper.h:1021): drop the corrections of the last solve only */

@@ -138,7 +138,58 @@ def make_trajectory(seed: int, n_scans: int, step: float = 0.5):
     return ranges, odom, traj
 
 
+def lifecycle_inprocess():
+    """Adapter hardening checks that need the integration library in this process: option mapping of B200Solver (the ceres_* keys
+    CeresSolver::Configure reads) and release of the matchers' device state on Mapper::Reset / destruction."""
+    L = C.CDLL(library("b200"))
+    L.krep_create.restype = C.c_void_p
+    L.krep_create.argtypes = [C.c_int]
+    L.krep_process.argtypes = [C.c_void_p, _DP, C.c_int, _DP, C.c_int]
+    L.krep_set.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    L.krep_solver_configure.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    L.krep_reset_mapper.argtypes = [C.c_void_p]
+    L.krep_destroy.argtypes = [C.c_void_p]
+    L.b200_shim_live_handles.restype = C.c_long
+    L.krep_init_laser.argtypes = [C.c_double] * 6
+    L.krep_init_laser(math.radians(-135), math.radians(135), math.radians(0.25), 0.1, 30.0, 12.0)
+    ranges, odom, _ = make_trajectory(3, 24)
+    h = L.krep_create(1)
+    for k, v in YAML_PARAMS.items():
+        L.krep_set(h, k.encode(), float(v))
+    out = {"configure": {}}
+    for key, val in (("ceres_loss_function", "HuberLoss"), ("ceres_loss_function", "CauchyLoss"), ("ceres_loss_function", "None"),
+                     ("ceres_loss_function", "Bogus"), ("ceres_trust_strategy", "LEVENBERG_MARQUARDT"), ("ceres_trust_strategy", "DOGLEG"),
+                     ("ceres_linear_solver", "SPARSE_NORMAL_CHOLESKY"), ("ceres_preconditioner", "SCHUR_JACOBI"), ("no_such_key", "1")):
+        out["configure"][f"{key}={val}"] = int(L.krep_solver_configure(h, key.encode(), val.encode()))
+    live = [int(L.b200_shim_live_handles())]
+
+    def feed(lo, hi):
+        for i in range(lo, hi):
+            L.krep_process(h, np.ascontiguousarray(ranges[i]).ctypes.data_as(_DP), ranges.shape[1], np.ascontiguousarray(odom[i]).ctypes.data_as(_DP), i)
+    feed(0, 12)
+    live.append(int(L.b200_shim_live_handles()))     # sequential + loop matcher
+    L.krep_reset_mapper(h)
+    live.append(int(L.b200_shim_live_handles()))     # Mapper::Reset deleted both
+    feed(12, 24)
+    live.append(int(L.b200_shim_live_handles()))
+    L.krep_destroy(h)
+    live.append(int(L.b200_shim_live_handles()))
+    out["live_handles"] = live
+    return out
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "lifecycle":
+        import json
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        try:
+            res = lifecycle_inprocess()
+        finally:
+            os.dup2(saved, 1)
+        print(json.dumps(res))
+        sys.exit(0)
     which, fin, fout = sys.argv[1], sys.argv[2], sys.argv[3]
     z = np.load(fin)
     params = {str(k): float(v) for k, v in zip(z["pkeys"], z["pvals"])}

@@ -59,6 +59,26 @@ void * krep_create(int use_solver)
   return r;
 }
 
+// B200Solver::ConfigureFromStrings (the mapping CeresSolver::Configure applies to the ceres_* ROS parameters): returns the
+// number of keys applied, -1 without a solver
+int krep_solver_configure(void * rp, const char * key, const char * value)
+{
+  Replay * r = static_cast<Replay *>(rp);
+  if (!r->solver) return -1;
+  return r->solver->ConfigureFromStrings({{std::string(key), std::string(value)}});
+}
+
+// Mapper::Reset (Mapper.cpp:2656-2677) deletes both scan matchers; krep_destroy deletes the mapper.  With the matcher shim
+// linked, b200_shim_live_handles() must drop to 0 afterwards (no leaked device state).
+void krep_reset_mapper(void * rp) { static_cast<Replay *>(rp)->mapper.Reset(); }
+void krep_destroy(void * rp)
+{
+  Replay * r = static_cast<Replay *>(rp);
+  solver_plugins::B200Solver * s = r->solver;
+  delete r;
+  delete s;
+}
+
 int krep_set(void * rp, const char * name, double v)
 {
   Mapper * m = &static_cast<Replay *>(rp)->mapper;

@@ -7,6 +7,7 @@
 // reference's Mapper / MapperGraph performs -- sequential match, near-chain links, loop closure --
 // to the GPU, with no change to the reference sources.
 #include <cstdio>
+#include <mutex>
 #include <stdexcept>
 #include <unordered_map>
 #include <vector>
@@ -21,6 +22,16 @@ std::unordered_map<const ScanMatcher *, b200sm *> & handles()
 {
   static std::unordered_map<const ScanMatcher *, b200sm *> h;
   return h;
+}
+std::mutex & handles_mutex()
+{
+  static std::mutex m;
+  return m;
+}
+b200sm * handle_of(const ScanMatcher * m)
+{
+  std::lock_guard<std::mutex> lock(handles_mutex());
+  return handles().at(m);
 }
 long g_match_calls = 0;
 
@@ -41,6 +52,37 @@ inline LocalizedRangeScan * deref(LocalizedRangeScanMap::const_iterator it) { re
 }  // namespace
 
 extern "C" long b200_shim_match_calls() { return g_match_calls; }
+extern "C" long b200_shim_live_handles()
+{
+  std::lock_guard<std::mutex> lock(handles_mutex());
+  return static_cast<long>(handles().size());
+}
+
+// Releases the device state of a matcher.  Called by the destructor below; also exported for hosts that tear the mapper
+// down through other paths.
+extern "C" void b200_shim_release(const void * matcher)
+{
+  b200sm * h = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(handles_mutex());
+    auto it = handles().find(static_cast<const ScanMatcher *>(matcher));
+    if (it == handles().end()) return;
+    h = it->second;
+    handles().erase(it);
+  }
+  b200sm_destroy(h);
+}
+
+// ScanMatcher::~ScanMatcher (Mapper.cpp:464-475) is a strong symbol in Mapper.o; this definition is linked first (like
+// Create, -Wl,--allow-multiple-definition), frees what the reference's destructor frees -- nothing is allocated on this
+// path, the three members stay NULL -- and releases the b200sm handle, so Mapper::Reset / lifelong mode do not leak.
+ScanMatcher::~ScanMatcher()
+{
+  if (m_pCorrelationGrid) delete m_pCorrelationGrid;
+  if (m_pSearchSpaceProbs) delete m_pSearchSpaceProbs;
+  if (m_pGridLookup) delete m_pGridLookup;
+  b200_shim_release(this);
+}
 
 ScanMatcher * ScanMatcher::Create(Mapper * pMapper, kt_double searchSize, kt_double resolution,
                                   kt_double smearDeviation, kt_double rangeThreshold)
@@ -56,7 +98,14 @@ ScanMatcher * ScanMatcher::Create(Mapper * pMapper, kt_double searchSize, kt_dou
     return NULL;   // Mapper.cpp:481-493 returns NULL on invalid parameters
   }
   ScanMatcher * m = new ScanMatcher(pMapper);
-  handles()[m] = h;
+  b200sm * stale = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(handles_mutex());
+    auto it = handles().find(m);
+    if (it != handles().end()) stale = it->second;   // a matcher freed without its destructor reused the address
+    handles()[m] = h;
+  }
+  if (stale) b200sm_destroy(stale);
   return m;
 }
 
@@ -72,7 +121,7 @@ kt_double ScanMatcher::MatchScan(LocalizedRangeScan * pScan, const T & rBaseScan
   }
   const b200_scan q = to_scan(pScan);
   double mean[3], cov[9], resp = 0.0;
-  if (b200sm_match(handles().at(this), &q, base.data(), static_cast<int32_t>(base.size()), doPenalize ? 1 : 0,
+  if (b200sm_match(handle_of(this), &q, base.data(), static_cast<int32_t>(base.size()), doPenalize ? 1 : 0,
                    doRefineMatch ? 1 : 0, mean, cov, &resp) != B200_OK) {
     throw std::runtime_error(b200_last_error());   // the reference throws std::runtime_error too (Mapper.cpp:789-828)
   }

@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 raise RuntimeError(f"nvcc failed for {unit}:\n{r.stdout}\n{r.stderr}")
             rebuilt = True
     if rebuilt or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [nvcc] + ARCH + ["-shared", "--cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-o", LIB] + objs
+        cmd = [nvcc] + ARCH + ["-shared", "--cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64", "-o", LIB] + objs + ["-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -2,6 +2,7 @@
 // wrappers for device / pinned-host buffers.  No compute lives here.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstddef>
 #include <cstdint>
@@ -30,6 +31,15 @@ struct CudaFail {
 
 // Fails loudly (B200_ERR_CUDA) when there is no sm_100 device: there is no CPU fallback.
 void require_device();
+
+// NVTX range (shows up in Nsight Systems / ncu --nvtx; a no-op without an attached tool): upload / run / fetch of a sweep,
+// single matches, LM iterations of a solve ("tracing")
+struct NvtxRange {
+  explicit NvtxRange(const char * name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange & operator=(const NvtxRange &) = delete;
+};
 
 template <class T>
 struct DevBuf {

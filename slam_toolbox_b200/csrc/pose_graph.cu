@@ -1345,6 +1345,7 @@ struct Lm {
 static int solve(b200pg * h, b200pg_summary * sum)
 {
   const auto t_enter = std::chrono::steady_clock::now();
+  NvtxRange nvtx_solve("b200pg solve");
   const b200pg_opts & o = h->o;
   b200pg_summary S{};
   S.usable = 1;
@@ -1554,6 +1555,7 @@ static int solve(b200pg * h, b200pg_summary * sum)
     if (step_successful && gmax <= o.gradient_tolerance) { S.termination = 1; break; }
     if (radius <= o.min_trust_region_radius) { S.termination = 4; break; }
     ++it;
+    NvtxRange nvtx_it("b200pg LM iteration");
     step_successful = false;
     // LevenbergMarquardtStrategy::ComputeStep
     if (!reuse_diagonal) { k_pg_diag<<<L.blocksN, kPgThreads, 0, st>>>(d, o.min_lm_diagonal, o.max_lm_diagonal); L.launched(); }
@@ -1699,6 +1701,27 @@ void b200pg_destroy(b200pg * h)
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
+}
+
+static bool valid_opts(const b200pg_opts & o)
+{
+  return !(o.max_num_iterations < 0 || !(o.pcg_tolerance > 0) || o.pcg_max_iterations <= 0 || !(o.initial_trust_region_radius > 0) ||
+           o.loss_function < 0 || o.loss_function > 2 || (o.loss_function != 0 && !(o.loss_scale > 0)));
+}
+
+int b200pg_set_opts(b200pg * h, const b200pg_opts * opts)
+{
+  if (!h || !opts) return B200_ERR_INVALID_ARG;
+  if (!valid_opts(*opts)) { set_last_error("b200pg_set_opts: invalid options"); return B200_ERR_INVALID_ARG; }
+  h->o = *opts;
+  return B200_OK;
+}
+
+int b200pg_get_opts(const b200pg * h, b200pg_opts * opts)
+{
+  if (!h || !opts) return B200_ERR_INVALID_ARG;
+  *opts = h->o;
+  return B200_OK;
 }
 
 int b200pg_set_stream(b200pg * h, void * s)

@@ -574,6 +574,7 @@ static void do_raster(b200sm * h, const b200_scan * query, const b200_scan * bas
 double do_match(b200sm * h, const b200_scan * query, const b200_scan * base, int nbase, bool pen, bool refine,
                        double mean[3], double cov[9])
 {
+  NvtxRange nvtx_("b200sm match");
   for (int i = 0; i < 9; ++i) cov[i] = 0.0;
   if (query->n == 0) {   // M.cpp:547-557
     mean[0] = query->sensor_pose[0]; mean[1] = query->sensor_pose[1]; mean[2] = query->sensor_pose[2];

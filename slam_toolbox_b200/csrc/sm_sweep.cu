@@ -745,6 +745,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
                         const int32_t * chain_start, int nchains, const int32_t * pair_query,
                         const int32_t * pair_chain, int npairs, bool do_penalize)
 {
+  NvtxRange nvtx_("b200sm sweep upload");
   SweepHost & S = h->sweep;
   S.uploaded = S.ran = false;
   S.zero_done.clear();
@@ -1115,6 +1116,7 @@ static int sweep_kernel_choice(const b200sm * h, const SweepHost & S)
 
 static int sweep_run(b200sm * h)
 {
+  NvtxRange nvtx_("b200sm sweep run");
   SweepHost & S = h->sweep;
   if (!S.uploaded) { set_last_error("sweep: nothing uploaded"); return B200_ERR_INVALID_ARG; }
   cudaStream_t st = h->stream;
@@ -1221,6 +1223,7 @@ static void chain_of_pair(const SweepHost & S, int pair, const b200_scan *& base
 
 static int sweep_fetch(b200sm * h, bool do_refine, double * response, double * mean, double * cov)
 {
+  NvtxRange nvtx_("b200sm sweep fetch");
   SweepHost & S = h->sweep;
   if (!S.ran) { set_last_error("sweep: run before fetch"); return B200_ERR_INVALID_ARG; }
   if (!response || !mean || !cov) return B200_ERR_INVALID_ARG;

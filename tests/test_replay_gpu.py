@@ -44,3 +44,18 @@ def test_replay_with_the_shipped_yaml_parameters_order_dependent_raster():
     a = replay.run("ref", ranges, odom, replay.YAML_PARAMS)
     b = replay.run("b200", ranges, odom, replay.YAML_PARAMS)
     assert a["scans"] == b["scans"] and np.array_equal(a["poses"], b["poses"]) and a["edges"] == b["edges"]
+
+
+def test_adapter_option_mapping_and_handle_lifetime():
+    """B200Solver::ConfigureFromStrings maps the ceres_* keys of CeresSolver::Configure (solvers/ceres_solver.cpp:25-193); the matcher
+    shim's ~ScanMatcher releases the device state when Mapper::Reset / ~Mapper delete the matchers (no leak, no stale aliases)."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "replay.py"), "lifecycle"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    c = out["configure"]
+    assert c["ceres_loss_function=HuberLoss"] == 1 and c["ceres_loss_function=CauchyLoss"] == 1 and c["ceres_loss_function=None"] == 1
+    assert c["ceres_loss_function=Bogus"] == 0 and c["ceres_trust_strategy=DOGLEG"] == 0 and c["no_such_key=1"] == 0
+    assert c["ceres_trust_strategy=LEVENBERG_MARQUARDT"] == 1 and c["ceres_linear_solver=SPARSE_NORMAL_CHOLESKY"] == 1
+    assert out["live_handles"] == [0, 2, 0, 2, 0], out["live_handles"]

@@ -338,6 +338,7 @@ def seq_match_bench(n_matches: int, with_cpu: bool):
         for q, b in blocks:
             sm.MatchScan(q, b, True, True)
         l0 = sm.launch_count()
+        sm.match_timing(reset=True)
         t = time.perf_counter()
         res = []
         for i in range(n_matches):
@@ -345,7 +346,8 @@ def seq_match_bench(n_matches: int, with_cpu: bool):
             res.append(sm.MatchScan(q, b, True, True))
         gpu_ms = 1e3 * (time.perf_counter() - t) / n_matches
         row = {"grid": "%dx%d u8" % (grid_geometry(grid)[1], grid_geometry(grid)[1]), "search": "51x51x6 coarse + 3x3x11 fine",
-               "gpu_ms_per_match_e2e": gpu_ms, "gpu_matches_per_s": 1e3 / gpu_ms, "launches_per_match": (sm.launch_count() - l0) / n_matches}
+               "gpu_ms_per_match_e2e": gpu_ms, "gpu_matches_per_s": 1e3 / gpu_ms, "launches_per_match": (sm.launch_count() - l0) / n_matches,
+               "host_phases_ms": {k: round(float(v), 4) for k, v in sm.match_timing().items() if k != "matches"}}
         sm.close()
         if with_cpu:
             from oracle import karto_port as P

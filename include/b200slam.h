@@ -173,6 +173,9 @@ int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_b
  * kernel; "sweep_cluster" = CTAs per pair of the tiled kernel (0 auto, 1, 2, 4, 8); "sweep_chunks" = minimum number of angle chunks (0 auto).
  * All variants produce identical results. */
 int b200sm_set_option(b200sm * h, const char * name, int32_t value);
+/* Accumulated host wall time (ms) of the single-match path's phases since the last reset: out = {valid points + occupancy
+ * replay, raster upload + stamp, lookup-table build, volume (H2D, kernel, D2H, wait), FP64 epilogue, number of matches}. */
+int b200sm_match_timing(b200sm * h, double out[6], int32_t reset);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t b200sm_launch_count(const b200sm * h);
 

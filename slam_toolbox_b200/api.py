@@ -116,6 +116,7 @@ def lib():
     L.b200sm_batch_reduce_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.b200sm_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]
     L.b200sm_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+    L.b200sm_match_timing.argtypes = [C.c_void_p, _DP, C.c_int32]
     L.b200sm_launch_count.restype = C.c_int64
     L.b200sm_launch_count.argtypes = [C.c_void_p]
     if hasattr(L, "b200pg_create"):
@@ -404,6 +405,13 @@ class ScanMatcher:
 
     def launch_count(self) -> int:
         return int(lib().b200sm_launch_count(self._h))
+
+    def match_timing(self, reset: bool = False):
+        """Per-phase host wall time of the single-match path, averaged per match (ms)."""
+        t = np.zeros(6)
+        _check(lib().b200sm_match_timing(self._h, _dp(t), int(reset)))
+        n = max(t[5], 1.0)
+        return dict(valid_points=t[0] / n, raster=t[1] / n, lookup_tables=t[2] / n, volume=t[3] / n, epilogue=t[4] / n, matches=int(t[5]))
 
 
 class ScanSolver:

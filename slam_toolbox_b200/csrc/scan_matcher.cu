@@ -12,6 +12,7 @@
 // Compile with -fmad=false (device) and -ffp-contract=off (host): every double expression
 // below must round exactly like the reference's x86-64 build.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -87,26 +88,62 @@ __global__ void k_stamp(uint8_t * __restrict__ grid, int stride, int roi_x, int 
 }
 
 // ScanMatcher::GetResponse numerators (M.cpp:1172-1208) for every (pose, angle):
-// sums[p * nA + a] = sum_i grid[pos[p] + off[a][i]], skipping invalid beams and indices outside
-// [0, data_size).  One thread per (angle, pose); the angle's lookup row sits in shared memory.
-__global__ void k_correlate(const uint8_t * __restrict__ grid, int data_size,
-                            const int32_t * __restrict__ offsets, const int32_t * __restrict__ pos,
-                            int P, int nA, int n, int32_t * __restrict__ sums)
+// sums[p * nA + a] = sum_i grid[pos[p] + off[a][i]], skipping invalid beams and indices outside [0, data_size).
+// The grid (6.3 MB at the sequential matcher's 0.01 m) lives in global memory / L2, so a lookup costs an L2 round trip and the
+// kernel is bound by how many of them are in flight, not by bandwidth: a block takes 32 consecutive poses of one angle (the
+// lanes -- consecutive poses are 2 cells apart, so one warp load touches 1-2 sectors per grid row) and splits the beams over
+// its kCorrWarps warps (interleaved), each lane keeping 8 loads in flight; the partial sums meet in shared memory.
+// Round 1's kernel ran one thread per pose over all 1081 beams: 70 us for the 51 x 51 x 6 coarse pass at 6 % occupancy.
+constexpr int kCorrWarps = 8;
+__global__ void __launch_bounds__(32 * kCorrWarps) k_correlate(const uint8_t * __restrict__ grid, int data_size,
+                                                               const int32_t * __restrict__ offsets, const int32_t * __restrict__ pos,
+                                                               int P, int nA, int n, int32_t * __restrict__ sums)
 {
   extern __shared__ int32_t s_off[];
-  const int a = blockIdx.y;
+  __shared__ int s_part[kCorrWarps][32];
+  const int a = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s_off[i] = offsets[(size_t)a * n + i];
   __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const int base = pos[p];
+  const int p = blockIdx.x * 32 + lane;
   int acc = 0;
+  if (p < P) {
+    const int base = pos[p];
 #pragma unroll 8
-  for (int i = 0; i < n; ++i) {
-    int idx = base + s_off[i];
+    for (int i = warp; i < n; i += kCorrWarps) {
+      const int idx = base + s_off[i];
+      if ((unsigned)idx < (unsigned)data_size) acc += __ldg(grid + idx);
+    }
+  }
+  s_part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && p < P) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kCorrWarps; ++w) t += s_part[w][lane];
+    sums[(size_t)p * nA + a] = t;
+  }
+}
+
+// The same numerators for a handful of poses (the fine pass: 3 x 3 poses x 11 angles): one warp per (pose, angle), the lanes
+// split the beams.
+__global__ void __launch_bounds__(256) k_correlate_few(const uint8_t * __restrict__ grid, int data_size,
+                                                       const int32_t * __restrict__ offsets, const int32_t * __restrict__ pos,
+                                                       int P, int nA, int n, int32_t * __restrict__ sums)
+{
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= P * nA) return;
+  const int p = item / nA, a = item - p * nA;
+  const int base = pos[p];
+  const int32_t * off = offsets + (size_t)a * n;
+  int acc = 0;
+#pragma unroll 4
+  for (int i = lane; i < n; i += 32) {
+    const int idx = base + off[i];
     if ((unsigned)idx < (unsigned)data_size) acc += __ldg(grid + idx);
   }
-  sums[(size_t)p * nA + a] = acc;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) sums[(size_t)p * nA + a] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -478,8 +515,17 @@ double host_epilogue(const b200sm_params & prm, const GridGeom & geom, int probs
   return best;
 }
 
+// host-side phase timer of the single-match path (b200sm_match_timing): 0 cells (FindValidPoints + occupancy replay), 1 raster
+// upload + stamp, 2 plan build (lookup tables), 3 volume (H2D, kernel, D2H, wait), 4 epilogue, 5 matches
+struct PhaseTimer {
+  b200sm * h; int slot; std::chrono::steady_clock::time_point t0;
+  PhaseTimer(b200sm * hh, int s) : h(hh), slot(s), t0(std::chrono::steady_clock::now()) {}
+  ~PhaseTimer() { h->phase_ms[slot] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 static void upload_raster(b200sm * h, const std::vector<int32_t> & cells)
 {
+  PhaseTimer pt(h, 1);
   const GridGeom & g = h->g;
   h->ensure_stream();
   h->d_grid.reserve((size_t)g.data_size + 16);
@@ -526,12 +572,17 @@ static const int32_t * device_volume(b200sm * h, const CorrPlan & pl)
   h->d_offsets.reserve(noff + P);
   h->d_sums.reserve(total);
   B200_CUDA(cudaMemcpyAsync(h->d_offsets.p, h->h_stage_i.p, (noff + P) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-  const int threads = P >= 1024 ? 128 : 32;
-  dim3 grid((P + threads - 1) / threads, pl.nA);
-  size_t smem = (size_t)pl.n * sizeof(int32_t);
-  if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(k_correlate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_correlate<<<grid, threads, smem, h->stream>>>(h->d_grid.p, g.data_size, h->d_offsets.p, h->d_offsets.p + noff, P,
-                                                 pl.nA, pl.n, h->d_sums.p);
+  if (P * pl.nA <= 2048) {
+    const int items = P * pl.nA;
+    k_correlate_few<<<(items + 7) / 8, 256, 0, h->stream>>>(h->d_grid.p, g.data_size, h->d_offsets.p, h->d_offsets.p + noff, P, pl.nA,
+                                                           pl.n, h->d_sums.p);
+  } else {
+    dim3 grid((P + 31) / 32, pl.nA);
+    size_t smem = (size_t)pl.n * sizeof(int32_t);
+    if (smem > 40 * 1024) B200_CUDA(cudaFuncSetAttribute(k_correlate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_correlate<<<grid, 32 * kCorrWarps, smem, h->stream>>>(h->d_grid.p, g.data_size, h->d_offsets.p, h->d_offsets.p + noff, P,
+                                                           pl.nA, pl.n, h->d_sums.p);
+  }
   B200_CUDA(cudaGetLastError());
   h->launches++;
   B200_CUDA(cudaMemcpyAsync(h->h_sums.p, h->d_sums.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -544,14 +595,17 @@ static double correlate(b200sm * h, const b200_scan * q, const double center[3],
                         double mean[3], double cov[9], int32_t * sums_out, int32_t sums_cap, int32_t dims[3])
 {
   CorrPlan pl;
-  int rc = build_plan(h->g, h->probs_side, h->p, q, center, sp_off, sp_res, ang_off, ang_res, fine, pl);
+  int rc;
+  { PhaseTimer pt(h, 2); rc = build_plan(h->g, h->probs_side, h->p, q, center, sp_off, sp_res, ang_off, ang_res, fine, pl); }
   if (rc != B200_OK) throw CudaFail{rc};
-  const int32_t * sums = device_volume(h, pl);
+  const int32_t * sums;
+  { PhaseTimer pt(h, 3); sums = device_volume(h, pl); }
   if (dims) { dims[0] = pl.nX; dims[1] = pl.nY; dims[2] = pl.nA; }
   if (sums_out) {
     size_t total = (size_t)pl.nX * pl.nY * pl.nA;
     std::memcpy(sums_out, sums, std::min<size_t>(total, (size_t)std::max(0, sums_cap)) * sizeof(int32_t));
   }
+  PhaseTimer pt(h, 4);
   return host_epilogue(h->p, h->g, h->probs_side, pl, sums, do_penalize, mean, cov);
 }
 
@@ -567,7 +621,7 @@ static void do_raster(b200sm * h, const b200_scan * query, const b200_scan * bas
 {
   set_grid_offset(h->g, query);
   std::vector<int32_t> cells;
-  host_cells(h->g, h->cell_scratch, query, base, nbase, cells);
+  { PhaseTimer pt(h, 0); host_cells(h->g, h->cell_scratch, query, base, nbase, cells); }
   upload_raster(h, cells);
 }
 
@@ -575,6 +629,7 @@ double do_match(b200sm * h, const b200_scan * query, const b200_scan * base, int
                        double mean[3], double cov[9])
 {
   NvtxRange nvtx_("b200sm match");
+  h->phase_ms[5] += 1.0;
   for (int i = 0; i < 9; ++i) cov[i] = 0.0;
   if (query->n == 0) {   // M.cpp:547-557
     mean[0] = query->sensor_pose[0]; mean[1] = query->sensor_pose[1]; mean[2] = query->sensor_pose[2];
@@ -752,6 +807,14 @@ int b200sm_grid_copy(b200sm * h, uint8_t * out, int32_t cap)
 }
 
 int64_t b200sm_launch_count(const b200sm * h) { return h ? h->launches : 0; }
+
+int b200sm_match_timing(b200sm * h, double out[6], int32_t reset)
+{
+  if (!h || !out) return B200_ERR_INVALID_ARG;
+  for (int i = 0; i < 6; ++i) out[i] = h->phase_ms[i];
+  if (reset) for (int i = 0; i < 6; ++i) h->phase_ms[i] = 0.0;
+  return B200_OK;
+}
 
 int b200sm_set_option(b200sm * h, const char * name, int32_t value)
 {

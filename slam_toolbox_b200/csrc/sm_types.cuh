@@ -232,6 +232,7 @@ struct b200sm {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int64_t launches = 0;
+  double phase_ms[6] = {0, 0, 0, 0, 0, 0};   // host-side phase times of the single-match path (b200sm_match_timing)
   int probs_side = 0;   // Grid<double> m_pSearchSpaceProbs side (M.cpp:513)
 
   // single-match device state

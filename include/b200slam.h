@@ -165,6 +165,8 @@ int b200sm_batch_tile_info(b200sm * h, int32_t info[8]);
  * query), pairs handed one by one to the single-match path (tie list overflow with a non-zero best, response expansion),
  * pairs, 0}. */
 int b200sm_batch_fetch_stats(b200sm * h, int32_t stats[4]);
+/* Host wall time (ms) of the last upload: out = {per-query lookup tables (ComputeOffsets), descriptor tables of the kernel, whole call}. */
+int b200sm_batch_upload_timing(b200sm * h, double out[3]);
 /* bytes copied host->device by upload and device->host by fetch since the last reset */
 int b200sm_batch_transfer_bytes(b200sm * h, int64_t * h2d_bytes, int64_t * d2h_bytes, int32_t reset);
 /* Tuning / testing switches. "force_generic_sweep" = 1 runs batched sweeps on the generic kernel even

@@ -113,6 +113,7 @@ def lib():
     L.b200sm_batch_winners_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), _DP, _DP, _DP]
     L.b200sm_batch_tile_info.argtypes = [C.c_void_p, _IP]
     L.b200sm_batch_fetch_stats.argtypes = [C.c_void_p, _IP]
+    L.b200sm_batch_upload_timing.argtypes = [C.c_void_p, _DP]
     L.b200sm_batch_reduce_keys.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.b200sm_batch_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]
     L.b200sm_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
@@ -389,6 +390,11 @@ class ScanMatcher:
         _check(lib().b200sm_batch_tile_info(self._h, _ip(info)))
         return dict(available=bool(info[0]), cluster=int(info[1]), chunks=int(info[2]), bands=int(info[3]), band_rows=int(info[4]),
                     refused_reason=int(info[5]), clusters=int(info[6]), smem_kb=int(info[7]))
+
+    def batch_upload_timing(self):
+        t = np.zeros(3)
+        _check(lib().b200sm_batch_upload_timing(self._h, _dp(t)))
+        return dict(lookup_tables_ms=float(t[0]), kernel_tables_ms=float(t[1]), total_ms=float(t[2]))
 
     def batch_fetch_stats(self):
         st = np.zeros(4, dtype=np.int32)

@@ -7,6 +7,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 
 #include "../../include/b200slam.h"
@@ -40,6 +41,12 @@ struct NvtxRange {
   NvtxRange(const NvtxRange &) = delete;
   NvtxRange & operator=(const NvtxRange &) = delete;
 };
+
+// A small persistent pool of host threads for the table building on the host side of the ABI (lookup tables per angle,
+// FindValidPoints per base scan, descriptor lists per angle): parallel_for(n, fn) runs fn(0..n-1), the caller takes part.
+// B200_HOST_THREADS sets the size (default: up to 8, at most half the cores; 1 = everything on the calling thread).
+void host_parallel_for(int n, const std::function<void(int)> & fn);
+int host_pool_threads();
 
 template <class T>
 struct DevBuf {

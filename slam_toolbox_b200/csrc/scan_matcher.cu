@@ -15,8 +15,13 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <functional>
+#include <atomic>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -43,6 +48,106 @@ void require_device()
     throw CudaFail{B200_ERR_CUDA};
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// host thread pool
+// ------------------------------------------------------------------------------------------
+namespace {
+class HostPool {
+ public:
+  explicit HostPool(int workers)
+  {
+    for (int i = 0; i < workers; ++i) threads_.emplace_back([this] { loop(); });
+  }
+  ~HostPool()
+  {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; ++epoch_; epoch_a_.store(epoch_); }
+    cv_.notify_all();
+    for (auto & t : threads_) t.join();
+  }
+  int size() const { return (int)threads_.size() + 1; }
+  void run(int n, const std::function<void(int)> & fn)
+  {
+    if (n <= 0) return;
+    if (threads_.empty() || n == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::lock_guard<std::mutex> serial(run_m_);   // one parallel_for at a time (handles may be used from several threads)
+    {
+      std::lock_guard<std::mutex> l(m_);
+      fn_ = &fn; n_ = n; next_.store(0); done_.store(0); ++epoch_;
+      epoch_a_.store(epoch_, std::memory_order_release);
+    }
+    cv_.notify_all();
+    work();
+    // every index finished AND every worker out of work(): nobody can touch next_ / fn_ of this job any more
+    while (done_.load(std::memory_order_acquire) < n) std::this_thread::yield();
+    std::unique_lock<std::mutex> l(m_);
+    idle_.wait(l, [&] { return active_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work()
+  {
+    for (;;) {
+      const int i = next_.fetch_add(1);
+      if (i >= n_) break;
+      (*fn_)(i);
+      done_.fetch_add(1, std::memory_order_release);
+    }
+  }
+  void loop()
+  {
+    uint64_t seen = 0;
+    for (;;) {
+      // a burst of parallel_for calls (one match = valid points, two lookup tables, two epilogues) arrives within a few hundred
+      // microseconds: poll for that long before sleeping on the condition variable, whose wake-up costs 10-30 us per call
+      const auto spin_until = std::chrono::steady_clock::now() + std::chrono::microseconds(300);
+      while (epoch_a_.load(std::memory_order_acquire) == seen && std::chrono::steady_clock::now() < spin_until) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) return;
+        if (!fn_) continue;
+        ++active_;
+      }
+      work();
+      { std::lock_guard<std::mutex> l(m_); --active_; }
+      idle_.notify_all();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex m_, run_m_;
+  std::condition_variable cv_, idle_;
+  const std::function<void(int)> * fn_ = nullptr;
+  int n_ = 0, active_ = 0;
+  std::atomic<int> next_{0}, done_{0};
+  std::atomic<uint64_t> epoch_a_{0};   // copy of epoch_ for the lock-free poll
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+
+HostPool & pool()
+{
+  static HostPool p([] {
+    int want = 0;
+    if (const char * e = std::getenv("B200_HOST_THREADS")) want = std::atoi(e);
+    if (want <= 0) {
+      const int hw = (int)std::thread::hardware_concurrency();
+      want = std::max(1, std::min(8, hw / 2));
+    }
+    return want - 1;
+  }());
+  return p;
+}
+}  // namespace
+
+void host_parallel_for(int n, const std::function<void(int)> & fn) { pool().run(n, fn); }
+int host_pool_threads() { return pool().size(); }
 
 // ------------------------------------------------------------------------------------------
 // device helpers
@@ -244,9 +349,13 @@ static void host_cells(const GridGeom & g, CellScratch & sc, const b200_scan * q
 {
   cells.clear();
   const double vx = query->sensor_pose[0], vy = query->sensor_pose[1];
-  for (int b = 0; b < nbase; ++b) {
+  // FindValidPoints + WorldToGrid + ROI test are independent per base scan: one task each, concatenated in scan order
+  std::vector<std::vector<int32_t>> per(nbase);
+  auto one_scan = [&](int b) {
     const b200_scan & s = base[b];
-    if (s.n <= 0 || s.points_xy == nullptr) continue;   // NULL scans are skipped, M.cpp:1039
+    if (s.n <= 0 || s.points_xy == nullptr) return;   // NULL scans are skipped, M.cpp:1039
+    std::vector<int32_t> & out = per[b];
+    out.reserve((size_t)s.n);
     ValidPointState st;
     st.init();
     for (int i = 0; i < s.n; ++i) {
@@ -255,10 +364,12 @@ static void host_cells(const GridGeom & g, CellScratch & sc, const b200_scan * q
       for (int t = lo; t < hi; ++t) {
         int gx = world_to_grid(s.points_xy[2 * t], g.off_x, g.scale);
         int gy = world_to_grid(s.points_xy[2 * t + 1], g.off_y, g.scale);
-        if (is_up_to(gx, g.roi_w) && is_up_to(gy, g.roi_h)) cells.push_back(gx | (gy << 16));
+        if (is_up_to(gx, g.roi_w) && is_up_to(gy, g.roi_h)) out.push_back(gx | (gy << 16));
       }
     }
-  }
+  };
+  if (nbase >= 2) host_parallel_for(nbase, one_scan); else for (int b = 0; b < nbase; ++b) one_scan(b);
+  for (int b = 0; b < nbase; ++b) cells.insert(cells.end(), per[b].begin(), per[b].end());
   // AddScan's "cell already occupied" test (M.cpp:1093-1096): a point is dropped when its cell already holds 100,
   // i.e. lies in the 100-valued footprint of an earlier KEPT point (the centre only for most kernels; centre +
   // 4-neighbours for the shipped YAML smear). A bitmap over the full grid with lazy clearing replays it in O(points).
@@ -342,7 +453,7 @@ int build_plan(const GridGeom & g, int probs_side, const b200sm_params & prm, co
   }
   pl.angle.resize(pl.nA); pl.heading.resize(pl.nA); pl.angpen.resize(pl.nA);
   double startAngle = center[2] - ang_off;
-  for (int a = 0; a < pl.nA; ++a) {
+  auto one_angle = [&](int a) {
     double angle = startAngle + (uint32_t)a * ang_res;
     pl.angle[a] = angle;
     pl.heading[a] = normalize_angle(angle);
@@ -361,7 +472,9 @@ int build_plan(const GridGeom & g, int probs_side, const b200sm_params & prm, co
       pl.ogx[(size_t)a * n + i] = gx;
       pl.ogy[(size_t)a * n + i] = gy;
     }
-  }
+  };
+  if ((size_t)pl.nA * n >= 4096) host_parallel_for(pl.nA, one_angle);   // one angle = one task (disjoint rows of the tables)
+  else for (int a = 0; a < pl.nA; ++a) one_angle(a);
   // ---- pose arrays ----
   pl.xrel.resize(pl.nX); pl.newx.resize(pl.nX); pl.sqx.resize(pl.nX); pl.xs.resize(pl.nX); pl.px.resize(pl.nX);
   pl.yrel.resize(pl.nY); pl.newy.resize(pl.nY); pl.sqy.resize(pl.nY); pl.ys.resize(pl.nY); pl.py.resize(pl.nY);
@@ -411,36 +524,41 @@ int32_t device_offset(int32_t off, int data_size)
 // ScanMatcher::CorrelateScan's reduction (M.cpp:775-862) + both covariance routines, in FP64 on the
 // host, from the device's integer volume. sums index = (y*nX + x)*nA + a.
 double host_epilogue(const b200sm_params & prm, const GridGeom & geom, int probs_side, const CorrPlan & pl,
-                     const int32_t * sums, bool do_penalize, double mean[3], double cov[9])
+                     const int32_t * sums, bool do_penalize, double mean[3], double cov[9],
+                     const std::function<bool(int, int, int32_t *)> * extra_cell)
 {
   const int nX = pl.nX, nY = pl.nY, nA = pl.nA;
   const size_t total = (size_t)nX * nY * nA;
-  std::vector<double> resp(total);
+  static thread_local std::vector<double> resp_scratch, probs_scratch;
+  std::vector<double> & resp = resp_scratch;
+  resp.resize(total);
   const double norm = (double)((uint32_t)pl.n * (uint32_t)kOccupied);
-  for (int y = 0; y < nY; ++y)
-    for (int x = 0; x < nX; ++x)
+  const int side = probs_side;
+  std::vector<double> & probs = probs_scratch;
+  if (!pl.fine) probs.assign((size_t)side * side, 0.0);
+  // responses (M.cpp:670-685), the per-cell maximum image (M.cpp:781-799) and the best response, one search row per task.
+  // The distance penalty depends on (x, y) only: evaluated once per cell with the reference's expression -- same value.
+  std::vector<double> row_best((size_t)nY, -1.0);
+  auto one_row = [&](int y) {
+    double rb = -1;
+    for (int x = 0; x < nX; ++x) {
+      const double dp = do_penalize ? distance_penalty(pl.sqx[x], pl.sqy[y], prm.distance_variance_penalty, prm.minimum_distance_penalty) : 0.0;
+      double * cell = pl.fine ? nullptr : &probs[(size_t)pl.py[y] * side + pl.px[x]];
       for (int a = 0; a < nA; ++a) {
-        size_t k = ((size_t)y * nX + x) * nA + a;
+        const size_t k = ((size_t)y * nX + x) * nA + a;
         double r = 0.0;
         if (pl.n != 0) { r = (double)sums[k]; r /= norm; }
-        if (do_penalize && !double_equal(r, 0.0)) {
-          double dp = distance_penalty(pl.sqx[x], pl.sqy[y], prm.distance_variance_penalty, prm.minimum_distance_penalty);
-          r *= (dp * pl.angpen[a]);
-        }
+        if (do_penalize && !double_equal(r, 0.0)) r *= (dp * pl.angpen[a]);
         resp[k] = r;
+        rb = maximum(rb, r);
+        if (cell) *cell = maximum(r, *cell);
       }
-  double best = -1;
-  std::vector<double> probs;
-  const int side = probs_side;
-  if (!pl.fine) probs.assign((size_t)side * side, 0.0);
-  for (size_t k = 0; k < total; ++k) {
-    best = maximum(best, resp[k]);
-    if (!pl.fine) {
-      size_t xy = k / nA;
-      double & c = probs[(size_t)pl.py[xy / nX] * side + pl.px[xy % nX]];
-      c = maximum(resp[k], c);
     }
-  }
+    row_best[y] = rb;
+  };
+  if (total >= 4096) host_parallel_for(nY, one_row); else for (int y = 0; y < nY; ++y) one_row(y);
+  double best = -1;
+  for (int y = 0; y < nY; ++y) best = maximum(best, row_best[y]);
   double ax = 0.0, ay = 0.0, thetaX = 0.0, thetaY = 0.0;
   int count = 0;
   for (size_t k = 0; k < total; ++k) {
@@ -487,18 +605,27 @@ double host_epilogue(const b200sm_params & prm, const GridGeom & geom, int probs
     for (int x = 0; x < nX; ++x) if (pl.xs[x] == gx) xi = x;
     for (int y = 0; y < nY; ++y) if (pl.ys[y] == gy) yi = y;
     double nrm = 0.0, acc = 0.0;
+    // the averaged best pose normally rounds to one of the searched cells; when the search centre sits on a half-cell boundary
+    // it can round to a cell in between (the reference calls GetResponse on whatever cell WorldToGrid gives, M.cpp:1003-1011):
+    // its nA sums are then computed on demand against the resident raster
+    std::vector<int32_t> extra;
+    const int32_t * col = nullptr;
     if (xi >= 0 && yi >= 0) {
+      col = sums + ((size_t)yi * nX + xi) * nA;
+    } else if (extra_cell) {
+      extra.assign(nA, 0);
+      if ((*extra_cell)(gx, gy, extra.data())) col = extra.data();
+    }
+    if (col) {
       for (int a = 0; a < nA; ++a) {
         double response = 0.0;
-        if (pl.n != 0) { response = (double)sums[((size_t)yi * nX + xi) * nA + a]; response /= norm; }
+        if (pl.n != 0) { response = (double)col[a]; response /= norm; }
         if (response >= (best - 0.1)) {
           nrm += response;
           acc += (square(pl.angle[a] - bestAngle) * response);
         }
       }
     } else {
-      // the averaged best pose always rounds to one of the searched cells (it lies in their convex
-      // hull); if it ever did not, say so instead of guessing
       set_last_error("fine-match best pose fell outside the searched cells");
       throw CudaFail{B200_ERR_UNSUPPORTED};
     }
@@ -606,7 +733,23 @@ static double correlate(b200sm * h, const b200_scan * q, const double center[3],
     std::memcpy(sums_out, sums, std::min<size_t>(total, (size_t)std::max(0, sums_cap)) * sizeof(int32_t));
   }
   PhaseTimer pt(h, 4);
-  return host_epilogue(h->p, h->g, h->probs_side, pl, sums, do_penalize, mean, cov);
+  const std::function<bool(int, int, int32_t *)> extra = [&](int gx, int gy, int32_t * out) {
+    // one more pose against the raster and lookup table that are still on the device
+    if (!is_up_to(gx, h->g.width) || !is_up_to(gy, h->g.height) || pl.n == 0) return false;
+    const size_t noff = (size_t)pl.nA * pl.n;
+    const int32_t posv = gx + gy * h->g.stride;
+    h->d_extra.reserve((size_t)pl.nA + 1);
+    B200_CUDA(cudaMemcpyAsync(h->d_extra.p + pl.nA, &posv, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    k_correlate_few<<<(pl.nA + 7) / 8, 256, 0, h->stream>>>(h->d_grid.p, h->g.data_size, h->d_offsets.p, h->d_extra.p + pl.nA, 1, pl.nA, pl.n,
+                                                           h->d_extra.p);
+    B200_CUDA(cudaGetLastError());
+    h->launches++;
+    (void)noff;
+    B200_CUDA(cudaMemcpyAsync(out, h->d_extra.p, (size_t)pl.nA * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    return true;
+  };
+  return host_epilogue(h->p, h->g, h->probs_side, pl, sums, do_penalize, mean, cov, &extra);
 }
 
 static void check_scan(const b200_scan * s, bool need_ranges)

@@ -9,6 +9,7 @@
 //   k_sweep_fine     3x3xnA fine volumes for do_refine                           (M.cpp:621-629)
 // Compile with -fmad=false / -ffp-contract=off (bit-exact FP64, see sm_math.cuh).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -746,6 +747,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
                         const int32_t * pair_chain, int npairs, bool do_penalize)
 {
   NvtxRange nvtx_("b200sm sweep upload");
+  const auto t_enter = std::chrono::steady_clock::now();
   SweepHost & S = h->sweep;
   S.uploaded = S.ran = false;
   S.zero_done.clear();
@@ -801,6 +803,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   S.max_n = std::max(max_n, 1);
 
   // ---- coarse plans, one per query ----
+  const auto t_plans0 = std::chrono::steady_clock::now();
   double off[2], res[2];
   coarse_search(h, off, res);
   S.plans.assign(nq, CorrPlan());
@@ -810,6 +813,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
                         h->p.coarse_search_angle_offset, h->p.coarse_angle_resolution, false, S.plans[q]);
     if (rc != B200_OK) return rc;
   }
+  const auto t_plans1 = std::chrono::steady_clock::now();
   const CorrPlan & p0 = S.plans[0];
   const int nX = p0.nX, nY = p0.nY, nA = p0.nA, P = nX * nY;
   {
@@ -952,10 +956,14 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   // chains of several scans: the tiled kernel's per-point raster is ~2x faster than the single-CTA kernel's per-tap one
   // (measured 186 k vs 97 k pairs/s at chain length 10); single scans: the single-CTA kernel is ~4 % ahead (4 raster stages, not 8)
   const bool long_chains = h->sweep_kernel == 0 && (size_t)nitems > 2 * (size_t)npairs;
+  const auto t_tab0 = std::chrono::steady_clock::now();
   bool have = false;
   if (!h->force_generic && h->sweep_kernel != 2 && !want_cluster && !long_chains) have = build_fast_tables(h, S, st);
   if (!h->force_generic && !have) have = build_tile_tables(h, S, st);
   if (!h->force_generic && !have && h->sweep_kernel == 2) build_fast_tables(h, S, st);
+  const auto t_tab1 = std::chrono::steady_clock::now();
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  S.upload_ms[0] = ms(t_plans0, t_plans1); S.upload_ms[1] = ms(t_tab0, t_tab1); S.upload_ms[2] = ms(t_enter, t_tab1);
   S.uploaded = true;
   return B200_OK;
 }
@@ -986,18 +994,25 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   int n_edge = 0;
   beams.reserve((size_t)nq * nA * n);
   mult.reserve((size_t)nq * nA * n);
+  // one angle's lists, built independently (one host-pool task per angle), then concatenated in angle order
+  struct AngleLists {
+    std::vector<uint16_t> beams, mult;
+    int32_t cs[33];                          // relative to the angle's first descriptor
+    std::vector<int32_t> wgroup[4], egroup[16], slow;
+    int n_edge = 0;
+  };
+  std::vector<AngleLists> al(nA);
   for (int q = 0; q < nq; ++q) {
     const CorrPlan & pl = S.plans[q];
     for (int k = 1; k < nX; ++k) if (pl.xs[k] != pl.xs[0] + 2 * k) return bail(6);   // coarse step must be exactly 2 cells
     for (int k = 1; k < nY; ++k) if (pl.ys[k] != pl.ys[0] + 2 * k) return bail(7);
     const int X0 = pl.xs[0], Y0 = pl.ys[0];
-    std::vector<uint16_t> group[16];
-    std::vector<int32_t> wgroup[4], egroup[16];
-    for (int a = 0; a < nA; ++a) {
-      for (auto & v : group) v.clear();
-      for (auto & v : wgroup) v.clear();
-      for (auto & v : egroup) v.clear();
-      slow_start[(size_t)q * (nA + 1) + a] = (int32_t)slow.size();
+    auto one_angle = [&](int a) {
+      AngleLists & L = al[a];
+      std::vector<uint16_t> group[16];
+      L.beams.clear(); L.mult.clear(); L.slow.clear(); L.n_edge = 0;
+      for (auto & v : L.wgroup) v.clear();
+      for (auto & v : L.egroup) v.clear();
       for (int i = 0; i < n; ++i) {
         const int32_t off = pl.offsets[(size_t)a * n + i];
         if (off == kInvalidScan) continue;
@@ -1016,30 +1031,20 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
           const bool cols_hit = Xb + 2 * (nX - 1) >= 0 && Xb < g.stride;
           if (rows_hit && cols_hit) {
             const int c = Xb >> 1, r = Yb >> 1;   // arithmetic shifts: floor for negative coordinates
-            egroup[((Yb & 1) * 2 + (Xb & 1)) * 4 + (c & 3)].push_back((int32_t)((uint32_t)(r & 0xFFFF) | ((uint32_t)(c >> 2) << 16)));
-            ++n_edge;
+            L.egroup[((Yb & 1) * 2 + (Xb & 1)) * 4 + (c & 3)].push_back((int32_t)((uint32_t)(r & 0xFFFF) | ((uint32_t)(c >> 2) << 16)));
+            ++L.n_edge;
           }
           const bool wraps = Xb < 0 || Xb + 2 * (nX - 1) >= g.stride;
-          if (wraps && Yb + 2 * (nY - 1) + 1 >= 0 && Yb - 1 < g.height) wgroup[((Yb & 1) ^ 1) * 2 + (Xb & 1)].push_back(e);
+          if (wraps && Yb + 2 * (nY - 1) + 1 >= 0 && Yb - 1 < g.height) L.wgroup[((Yb & 1) ^ 1) * 2 + (Xb & 1)].push_back(e);
         } else {
           const int32_t dv = device_offset(off, g.data_size);
-          if (dv != kDevInvalid) slow.push_back(dv);   // FAR: can still index [0, data_size) for some pose
+          if (dv != kDevInvalid) L.slow.push_back(dv);   // FAR: can still index [0, data_size) for some pose
         }
       }
-      for (int k = 0; k < 4; ++k) {
-        wrap2_start[((size_t)q * nA + a) * 4 + k] = (int32_t)wrap2.size();
-        wrap2.insert(wrap2.end(), wgroup[k].begin(), wgroup[k].end());
-      }
-      for (int k = 0; k < 16; ++k) {
-        edge_start[((size_t)q * nA + a) * 17 + k] = (int32_t)edge.size();
-        edge.insert(edge.end(), egroup[k].begin(), egroup[k].end());
-      }
-      edge_start[((size_t)q * nA + a) * 17 + 16] = (int32_t)edge.size();
-      int32_t * cs = &cls_start[((size_t)q * nA + a) * 33];
       for (int k = 0; k < 16; ++k) {
         std::vector<uint16_t> & gk = group[k];
         std::sort(gk.begin(), gk.end());
-        cs[2 * k] = (int32_t)beams.size();
+        L.cs[2 * k] = (int32_t)L.beams.size();
         // run-length encode: beams that land in the same cell share a descriptor. Entries with multiplicity >= 3
         // go to the group's multi list (one load, fields multiplied), provided the whole group fits one flush.
         const bool dedup = !h->no_dedup && gk.size() <= (size_t)kFastChunk;
@@ -1051,14 +1056,35 @@ static bool build_fast_tables(b200sm * h, SweepHost & S, cudaStream_t st)
           if (dedup && cnt >= 3) {
             multi.emplace_back(gk[i], (uint16_t)cnt);
           } else {
-            for (size_t t = 0; t < cnt; ++t) { beams.push_back(gk[i]); mult.push_back(1); }
+            for (size_t t = 0; t < cnt; ++t) { L.beams.push_back(gk[i]); L.mult.push_back(1); }
           }
           i = j;
         }
-        cs[2 * k + 1] = (int32_t)beams.size();
-        for (auto & mk : multi) { beams.push_back(mk.first); mult.push_back(mk.second); }
+        L.cs[2 * k + 1] = (int32_t)L.beams.size();
+        for (auto & mk : multi) { L.beams.push_back(mk.first); L.mult.push_back(mk.second); }
       }
-      cs[32] = (int32_t)beams.size();
+      L.cs[32] = (int32_t)L.beams.size();
+    };
+    host_parallel_for(nA, one_angle);
+    for (int a = 0; a < nA; ++a) {
+      const AngleLists & L = al[a];
+      slow_start[(size_t)q * (nA + 1) + a] = (int32_t)slow.size();
+      slow.insert(slow.end(), L.slow.begin(), L.slow.end());
+      n_edge += L.n_edge;
+      for (int k = 0; k < 4; ++k) {
+        wrap2_start[((size_t)q * nA + a) * 4 + k] = (int32_t)wrap2.size();
+        wrap2.insert(wrap2.end(), L.wgroup[k].begin(), L.wgroup[k].end());
+      }
+      for (int k = 0; k < 16; ++k) {
+        edge_start[((size_t)q * nA + a) * 17 + k] = (int32_t)edge.size();
+        edge.insert(edge.end(), L.egroup[k].begin(), L.egroup[k].end());
+      }
+      edge_start[((size_t)q * nA + a) * 17 + 16] = (int32_t)edge.size();
+      int32_t * cs = &cls_start[((size_t)q * nA + a) * 33];
+      const int32_t base = (int32_t)beams.size();
+      for (int k = 0; k < 33; ++k) cs[k] = base + L.cs[k];
+      beams.insert(beams.end(), L.beams.begin(), L.beams.end());
+      mult.insert(mult.end(), L.mult.begin(), L.mult.end());
     }
     slow_start[(size_t)q * (nA + 1) + nA] = (int32_t)slow.size();
   }
@@ -1285,7 +1311,16 @@ static int sweep_fetch(b200sm * h, bool do_refine, double * response, double * m
   B200_CUDA(cudaStreamSynchronize(st));
   for (int p = 0; p < S.npairs; ++p) {
     if (done[p]) continue;
-    response[p] = host_epilogue(h->p, fg[p], h->probs_side, fp[p], hs + (size_t)p * P * nA, S.do_penalize, &mean[3 * p], &cov[9 * p]);
+    try {
+      response[p] = host_epilogue(h->p, fg[p], h->probs_side, fp[p], hs + (size_t)p * P * nA, S.do_penalize, &mean[3 * p], &cov[9 * p]);
+    } catch (const CudaFail & f) {
+      if (f.code != B200_ERR_UNSUPPORTED) throw;
+      // the averaged fine pose rounded to a cell outside the 3 x 3 searched ones: the single-match path evaluates that cell
+      const b200_scan * base; int nbase;
+      chain_of_pair(S, p, base, nbase);
+      response[p] = do_match(h, &S.queries[S.pair_query[p]], base, nbase, S.do_penalize, true, &mean[3 * p], &cov[9 * p]);
+      S.fallback_pairs++;
+    }
   }
   return B200_OK;
 }
@@ -1455,6 +1490,13 @@ int b200sm_batch_fetch_stats(b200sm * h, int32_t stats[4])
 {
   if (!h || !stats) return B200_ERR_INVALID_ARG;
   stats[0] = h->sweep.zero_pairs; stats[1] = h->sweep.fallback_pairs; stats[2] = h->sweep.npairs; stats[3] = 0;
+  return B200_OK;
+}
+
+int b200sm_batch_upload_timing(b200sm * h, double out[3])
+{
+  if (!h || !out) return B200_ERR_INVALID_ARG;
+  for (int i = 0; i < 3; ++i) out[i] = h->sweep.upload_ms[i];
   return B200_OK;
 }
 

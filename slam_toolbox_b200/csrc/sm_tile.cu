@@ -736,14 +736,19 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   std::vector<std::vector<uint16_t>> grp((size_t)nA * nstage * 4);
   std::vector<std::vector<int32_t>> egrp((size_t)nA * nstage * 4), wgrp((size_t)nA * nstage);
   blob.reserve((size_t)nq * nA * n * 2 + 4096);
+  struct Encoded { int32_t tbl[12]; std::vector<uint16_t> pay; };
+  std::vector<Encoded> enc((size_t)nA * nstage);
+  std::vector<std::vector<int32_t>> slow_a(nA);
+  std::vector<int> nfast_a(nA), nedge_a(nA);
   for (int q = 0; q < nq; ++q) {
     const CorrPlan & pl = S.plans[q];
     const int X0 = pl.xs[0], Y0 = pl.ys[0];
-    for (auto & v : grp) v.clear();
-    for (auto & v : egrp) v.clear();
-    for (auto & v : wgrp) v.clear();
-    for (int a = 0; a < nA; ++a) {
-      slow_start[(size_t)q * (nA + 1) + a] = (int32_t)slow.size();
+    // one host-pool task per angle: classify its beams, then sort / run-length encode its groups stage by stage
+    auto one_angle = [&](int a) {
+      for (int k = 0; k < nstage * 4; ++k) { grp[(size_t)a * nstage * 4 + k].clear(); egrp[(size_t)a * nstage * 4 + k].clear(); }
+      for (int k = 0; k < nstage; ++k) wgrp[(size_t)a * nstage + k].clear();
+      slow_a[a].clear();
+      int nf = 0, ne = 0;
       for (int i = 0; i < n; ++i) {
         const int32_t off = pl.offsets[(size_t)a * n + i];
         if (off == kInvalidScan) continue;
@@ -755,7 +760,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
           const int band = std::min(r / B, nbands - 1);
           const int wo = (r - band * B) * pitch_w + (c >> 2);
           grp[((size_t)a * nstage + (pq * 2 + pp) * nbands + band) * 4 + (c & 3)].push_back((uint16_t)wo);
-          ++n_fast;
+          ++nf;
         } else if (Xb >= -g.stride && Xb + 2 * (nX - 1) < 2 * g.stride && Xb > -32768 && Xb < 32767 && Yb > -32768 && Yb < 32767) {
           // EDGE beam: at most one row wrap.  Primary entry in the beam's own phase; if some column leaves [0, stride), a
           // secondary entry in the phase with the row parity flipped.
@@ -768,7 +773,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
             if (rr > -32768 && rr < 32767) {
               egrp[((size_t)a * nstage + ((Yb & 1) * 2 + (Xb & 1)) * nbands + band) * 4 + (c & 3)].push_back(
                 (int32_t)((uint32_t)(rr & 0xFFFF) | ((uint32_t)(c >> 2) << 16)));
-              ++n_edge;
+              ++ne;
             }
           }
           const bool wraps = Xb < 0 || Xb + 2 * (nX - 1) >= g.stride;
@@ -780,9 +785,52 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
           }
         } else {
           const int32_t dv = device_offset(off, g.data_size);
-          if (dv != kDevInvalid) slow.push_back(dv);   // FAR: can still index [0, data_size) for some pose
+          if (dv != kDevInvalid) slow_a[a].push_back(dv);   // FAR: can still index [0, data_size) for some pose
         }
       }
+      nfast_a[a] = nf; nedge_a[a] = ne;
+      // the angle's groups of every stage: table of (plain begin, multi begin, multi end) per alignment, relative to the
+      // angle's own payload (whose start is 4-entry aligned in the block), and the payload
+      for (int sg = 0; sg < nstage; ++sg) {
+        Encoded & E = enc[(size_t)a * nstage + sg];
+        std::vector<uint16_t> & pay = E.pay;
+        pay.clear();
+        for (int m = 0; m < 4; ++m) {
+          std::vector<uint16_t> & gk = grp[((size_t)a * nstage + sg) * 4 + m];
+          std::sort(gk.begin(), gk.end());
+          while (pay.size() & 3) pay.push_back(0);   // the plain list is read with 64-bit loads
+          const int pb = (int)pay.size();
+          // run-length encode: beams that land in the same cell share a descriptor.  Entries with multiplicity >= 3 go to the
+          // group's multi list (one load, fields multiplied), provided the whole group fits one flush.
+          const bool dedup = !h->no_dedup && gk.size() <= (size_t)kChunkBeams;
+          std::vector<std::pair<uint16_t, uint16_t>> multi;
+          for (size_t i = 0; i < gk.size();) {
+            size_t j = i;
+            while (j < gk.size() && gk[j] == gk[i]) ++j;
+            const size_t cnt = j - i;
+            if (dedup && cnt >= 3) multi.emplace_back(gk[i], (uint16_t)cnt);
+            else for (size_t t = 0; t < cnt; ++t) pay.push_back(gk[i]);
+            i = j;
+          }
+          // the multi list (offset, multiplicity pairs, read as 32-bit words) starts where the plain list ends: keep that
+          // index even by moving an odd plain list's last entry into the multi list with multiplicity 1
+          if (((int)pay.size() - pb) & 1) {
+            const uint16_t last = pay.back();
+            pay.pop_back();
+            multi.emplace_back(last, (uint16_t)1);
+          }
+          const int mb = (int)pay.size();
+          for (auto & mk : multi) { pay.push_back(mk.first); pay.push_back(mk.second); }
+          E.tbl[3 * m + 0] = pb; E.tbl[3 * m + 1] = mb; E.tbl[3 * m + 2] = (int)pay.size();
+        }
+        while (pay.size() & 3) pay.push_back(0);
+      }
+    };
+    host_parallel_for(nA, one_angle);
+    for (int a = 0; a < nA; ++a) {
+      slow_start[(size_t)q * (nA + 1) + a] = (int32_t)slow.size();
+      slow.insert(slow.end(), slow_a[a].begin(), slow_a[a].end());
+      n_fast += nfast_a[a]; n_edge += nedge_a[a];
     }
     slow_start[(size_t)q * (nA + 1) + nA] = (int32_t)slow.size();
     for (int a = 0; a < nA; ++a)
@@ -796,41 +844,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
           edge.insert(edge.end(), ev.begin(), ev.end());
         }
       }
-    // one angle's groups of one stage: table of (plain begin, multi begin, multi end) per alignment, relative to the angle's
-    // own payload (whose start is 4-entry aligned in the block), and the payload
-    auto encode_angle = [&](int a, int sg, int32_t tbl[12], std::vector<uint16_t> & pay) {
-      pay.clear();
-      for (int m = 0; m < 4; ++m) {
-        std::vector<uint16_t> & gk = grp[((size_t)a * nstage + sg) * 4 + m];
-        std::sort(gk.begin(), gk.end());
-        while (pay.size() & 3) pay.push_back(0);   // the plain list is read with 64-bit loads
-        const int pb = (int)pay.size();
-        // run-length encode: beams that land in the same cell share a descriptor.  Entries with multiplicity >= 3 go to the
-        // group's multi list (one load, fields multiplied), provided the whole group fits one flush.
-        const bool dedup = !h->no_dedup && gk.size() <= (size_t)kChunkBeams;
-        std::vector<std::pair<uint16_t, uint16_t>> multi;
-        for (size_t i = 0; i < gk.size();) {
-          size_t j = i;
-          while (j < gk.size() && gk[j] == gk[i]) ++j;
-          const size_t cnt = j - i;
-          if (dedup && cnt >= 3) multi.emplace_back(gk[i], (uint16_t)cnt);
-          else for (size_t t = 0; t < cnt; ++t) pay.push_back(gk[i]);
-          i = j;
-        }
-        // the multi list (offset, multiplicity pairs, read as 32-bit words) starts where the plain list ends: keep that
-        // index even by moving an odd plain list's last entry into the multi list with multiplicity 1
-        if (((int)pay.size() - pb) & 1) {
-          const uint16_t last = pay.back();
-          pay.pop_back();
-          multi.emplace_back(last, (uint16_t)1);
-        }
-        const int mb = (int)pay.size();
-        for (auto & mk : multi) { pay.push_back(mk.first); pay.push_back(mk.second); }
-        tbl[3 * m + 0] = pb; tbl[3 * m + 1] = mb; tbl[3 * m + 2] = (int)pay.size();
-      }
-      while (pay.size() & 3) pay.push_back(0);
-    };
-    std::vector<uint16_t> pay_a, pay;
+    std::vector<uint16_t> pay;
     std::vector<int32_t> tbl;
     for (int r = 0; r < C; ++r) {
       seq_start[(size_t)q * C + r] = (int32_t)seq.size();
@@ -844,17 +858,16 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
             tbl.clear(); pay.clear();
             int na = 0;
             while (a + na < ca0 + cna) {
-              int32_t t1[12];
-              encode_angle(a + na, sg, t1, pay_a);
+              const Encoded & E = enc[(size_t)(a + na) * nstage + sg];
               const size_t hdr = (((size_t)(na + 1) * 52) + 15) & ~(size_t)15;
-              const size_t bytes = (hdr + (pay.size() + pay_a.size()) * 2 + 15) & ~(size_t)15;
+              const size_t bytes = (hdr + (pay.size() + E.pay.size()) * 2 + 15) & ~(size_t)15;
               if (bytes > (size_t)stage_bytes) {
                 if (na > 0) break;
                 return bail(8);   // one angle does not fit the staging buffer
               }
               const int shift = (int)pay.size();
-              for (int k = 0; k < 12; ++k) tbl.push_back(t1[k] + shift);
-              pay.insert(pay.end(), pay_a.begin(), pay_a.end());
+              for (int k = 0; k < 12; ++k) tbl.push_back(E.tbl[k] + shift);
+              pay.insert(pay.end(), E.pay.begin(), E.pay.end());
               ++na;
             }
             const size_t hdr = (((size_t)na * 52) + 15) & ~(size_t)15;

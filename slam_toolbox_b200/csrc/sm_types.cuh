@@ -2,6 +2,7 @@
 // and sm_sweep.cu (batched loop-closure sweep).
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <utility>
 #include <vector>
 
@@ -218,6 +219,7 @@ struct SweepHost {
   int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes moved by upload / fetch since the last reset
   // pairs of the last fetch finished by the all-poses-tie closed form / handed to the single-match path
   int zero_pairs = 0, fallback_pairs = 0;
+  double upload_ms[3] = {0, 0, 0};   // host wall time of the last upload: lookup tables (plans), kernel tables, whole call
   std::vector<char> zero_done;
   std::vector<double> zero_mean, zero_cov;
   void release();
@@ -237,7 +239,7 @@ struct b200sm {
 
   // single-match device state
   b200::DevBuf<uint8_t> d_grid, d_kernel;
-  b200::DevBuf<int32_t> d_cells, d_offsets, d_sums;
+  b200::DevBuf<int32_t> d_cells, d_offsets, d_sums, d_extra;
   b200::PinBuf<int32_t> h_stage_i, h_sums;
   bool have_raster = false;
   b200::CellScratch cell_scratch;
@@ -274,5 +276,6 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st);
 void sweep_stage_h2d(void * dst, const void * src, size_t bytes, cudaStream_t s);
 void launch_sweep_tile(b200sm * h, SweepHost & S, cudaStream_t st);
 double host_epilogue(const b200sm_params & prm, const GridGeom & geom, int probs_side, const CorrPlan & pl,
-                     const int32_t * sums, bool do_penalize, double mean[3], double cov[9]);
+                     const int32_t * sums, bool do_penalize, double mean[3], double cov[9],
+                     const std::function<bool(int, int, int32_t *)> * extra_cell = nullptr);
 }  // namespace b200

@@ -24,4 +24,4 @@ for _ in range(10):
     sm.batch_fetch(); t3 = time.perf_counter()
     sm.MatchScanBatch(q, c, cs, None, False, False); t4 = time.perf_counter()
     T["upload"].append(t1 - t0); T["run+sync"].append(t2 - t1); T["fetch"].append(t3 - t2); T["fused"].append(t4 - t3)
-print({k: round(1e3 * float(np.median(v)), 3) for k, v in T.items()}, "kernel_ms", round(k, 3), sm.batch_info()["kernel"])
+print({k: round(1e3 * float(np.median(v)), 3) for k, v in T.items()}, "kernel_ms", round(k, 3), sm.batch_info()["kernel"], sm.batch_upload_timing())

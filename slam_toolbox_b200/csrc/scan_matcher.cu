@@ -373,7 +373,9 @@ static void host_cells(const GridGeom & g, CellScratch & sc, const b200_scan * q
   // AddScan's "cell already occupied" test (M.cpp:1093-1096): a point is dropped when its cell already holds 100,
   // i.e. lies in the 100-valued footprint of an earlier KEPT point (the centre only for most kernels; centre +
   // 4-neighbours for the shipped YAML smear). A bitmap over the full grid with lazy clearing replays it in O(points).
-  {
+  // With a kernel whose only 100 is its centre the rule drops exact duplicates of earlier cells: the max-stamp raster is the
+  // same with or without them, so the replay is skipped (it is most of this function's time).
+  if (g.order_dependent) {
     const int half = g.ksize / 2;
     const size_t nbits = (size_t)g.width * g.height;
     if (sc.bits.size() * 64 < nbits) sc.bits.assign((nbits + 63) / 64, 0);

@@ -800,7 +800,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
     S.h2d_bytes += (int64_t)(2 * npts * sizeof(double));
     B200_CUDA(cudaStreamSynchronize(st));   // h_d is reused for the per-query tables below
   }
-  S.max_n = std::max(max_n, 1);
+  S.max_n = (std::max(max_n, 1) + 3) & ~3;   // multiple of 4: every scan's cell list starts 16-byte aligned (bulk-copy staging)
 
   // ---- coarse plans, one per query ----
   const auto t_plans0 = std::chrono::steady_clock::now();

@@ -136,7 +136,8 @@ __device__ void tie_merge(TieRes & a, const double bL, const double bL2, const i
 }
 
 struct TileShared {
-  unsigned long long bar[2];
+  unsigned long long bar[4];       // [0..1] descriptor staging buffers, [2..3] cell-list staging buffers
+  uint8_t kern[256];               // the smear kernel's taps (when ksize^2 <= 256)
   int ctr[2];
   double dscratch[32];
   int iscratch[32];
@@ -178,9 +179,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
+    mbar_init(bar0 + 16, 1);
+    mbar_init(bar0 + 24, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     sh.ctr[0] = 0; sh.ctr[1] = 0;
   }
+  const bool kern_smem = taps <= 256;
+  if (kern_smem && tid < taps) sh.kern[tid] = d.kern[tid];
+  const uint8_t * kern = kern_smem ? sh.kern : d.kern;
   __syncthreads();
   if (C > 1) { cluster_arrive(); cluster_wait(); }   // every CTA of the cluster is running before any remote access
 
@@ -190,9 +196,19 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
     mbar_expect_tx(bar0 + 8 * buf, (uint32_t)e->bytes);
     bulk_g2s(stg0 + buf * (uint32_t)f.stage_bytes, f.desc + e->off, (uint32_t)e->bytes, bar0 + 8 * buf);
   };
+  // the valid-point cells of a pair's FIRST scan (what every stage's raster reads: 4.3 KB for 1081 beams) are staged in shared
+  // memory by a bulk copy too, one pair ahead -- a stage then starts without a global-memory round trip
+  const uint32_t cel0 = smem_u32(s_raw + f.off_cells);
+  const uint32_t cell_bytes = (uint32_t)f.cell_cap * 4u;
+  auto issue_cells = [&](int pr, uint32_t buf) {
+    const int it = min(d.pair_item_start[pr], max(d.nitems - 1, 0));
+    mbar_expect_tx(bar0 + 16 + 8 * buf, cell_bytes);
+    bulk_g2s(cel0 + buf * cell_bytes, d.cells + (size_t)it * d.max_n, cell_bytes, bar0 + 16 + 8 * buf);
+  };
   if (cluster_id < d.npairs && tid == 0) {
     const int q0 = d.pair_query[cluster_id];
     issue(f.seq + f.seq_start[q0 * C + rank], 0);
+    if (f.cell_cap) issue_cells(cluster_id, 0);
   }
 
   int iter = 0;
@@ -203,6 +219,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
     const int nseq = f.seq_start[q * C + rank + 1] - f.seq_start[q * C + rank];
     const int it0 = d.pair_item_start[pair], it1 = d.pair_item_start[pair + 1];
     bool first_chunk = true;
+    const int32_t * cells0 = d.cells + (size_t)it0 * d.max_n;
+    const int ncell0 = it0 < it1 ? d.cell_count[it0] : 0;   // read once per pair, not once per stage
+    if (f.cell_cap) {
+      if (tid == 0 && pair + nclusters < d.npairs) issue_cells(pair + nclusters, (uint32_t)((iter + 1) & 1));
+      mbar_wait(bar0 + 16 + 8 * (iter & 1), (uint32_t)((iter >> 1) & 1));
+      cells0 = reinterpret_cast<const int32_t *>(s_raw + f.off_cells + (size_t)(iter & 1) * cell_bytes);
+    }
 
     for (int si = 0; si < nseq; ++si) {
       const TileSeq e = seq[si];
@@ -223,8 +246,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
         // ---- raster: taps landing on (pp, pq) cells of this band (AddScan / SmearPoint, M.cpp:1080-1104, M.h:1152-1183);
         //      one thread per valid point, only the kernel rows / columns of this phase's parity ----
         for (int it = it0; it < it1; ++it) {
-          const int32_t * cl = d.cells + (size_t)it * d.max_n;
-          const int ncell = d.cell_count[it];
+          const int32_t * cl = it == it0 ? cells0 : d.cells + (size_t)it * d.max_n;
+          const int ncell = it == it0 ? ncell0 : d.cell_count[it];
           for (int t = tid; t < ncell; t += kTileThreads) {
             const int32_t cell = cl[t];
             if (cell < 0) continue;
@@ -233,7 +256,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
               const int rel = ((cy + ky) >> 1) - band_r0;
               if ((unsigned)rel >= (unsigned)f.alloc_rows) continue;
               for (int kx = (cx ^ pp) & 1; kx < d.ksize; kx += 2) {
-                const uint32_t kv = d.kern[ky * d.ksize + kx];
+                const uint32_t kv = kern[ky * d.ksize + kx];
                 if (kv) atomic_max_u8(S8 + rel * pitchB + ((cx + kx) >> 1), kv);
               }
             }
@@ -641,6 +664,9 @@ static int env_int(const char * name, int dflt)
   return (v && *v) ? std::atoi(v) : dflt;
 }
 
+// the first scan's cell list is staged when one list is small enough and its stride keeps the bulk copy 16-byte aligned
+static inline bool d_max_n_ok(int max_n) { return max_n > 0 && (max_n & 3) == 0 && max_n <= 4096; }
+
 static inline int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
 bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
@@ -721,7 +747,12 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   T.xtiles = xtiles; T.ytiles = ytiles; T.stage_bytes = stage_bytes;
   T.int_ties = (!S.do_penalize && (double)n * kOccupied < 0.9e6) ? 1 : 0;
   T.off_A = s_bytes; T.off_probs = s_bytes + a_bytes; T.off_stage = (T.off_probs + probs_bytes + 127) & ~(size_t)127;
-  const size_t smem = T.off_stage + 2 * (size_t)stage_bytes;
+  T.off_cells = T.off_stage + 2 * (size_t)stage_bytes;
+  // cell-list staging only where the chosen plan leaves room for it (it must not cost a band or a chunk: measured -17 % at 4 m / 20 m)
+  int cell_cap = d_max_n_ok(S.max_n) ? S.max_n : 0;                     // entries per cell staging buffer (0 = read cells from global)
+  if (T.off_cells + 2 * (size_t)cell_cap * 4 + sizeof(TileShared) + 64 > 227 * 1024) cell_cap = 0;
+  T.cell_cap = cell_cap;
+  const size_t smem = T.off_cells + 2 * (size_t)cell_cap * 4;
   if (smem + sizeof(TileShared) + 64 > 227 * 1024) return bail(5);
 
   // ---- per-query descriptor blocks and schedules ----

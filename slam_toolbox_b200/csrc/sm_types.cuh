@@ -162,7 +162,8 @@ struct TileDev {
   int xtiles, ytiles;
   int stage_bytes;               // size of one descriptor staging buffer
   int int_ties;                  // responses are monotone in the integer sum with spacing > tolerance: integer arg-max / ties
-  size_t off_A, off_probs, off_stage;   // byte offsets into dynamic shared memory (S at 0)
+  size_t off_A, off_probs, off_stage, off_cells;   // byte offsets into dynamic shared memory (S at 0)
+  int cell_cap;                  // entries of one cell-list staging buffer (= max_n), 0 = cells are read from global memory
   const uint8_t * desc;          // descriptor blob
   const TileSeq * seq;           // schedules
   const int32_t * seq_start;     // [nq * C + 1]

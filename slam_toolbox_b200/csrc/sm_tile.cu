@@ -89,6 +89,12 @@ __device__ __forceinline__ uint32_t dsmem_addr(const void * local, uint32_t rank
 }
 __device__ __forceinline__ void dsmem_st_f64(uint32_t a, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ void dsmem_st_s32(uint32_t a, int v) { asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ int dsmem_ld_s32(uint32_t a)
+{
+  int v;
+  asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ double dsmem_ld_f64(uint32_t a)
 {
   double v;
@@ -162,7 +168,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
   uint32_t * S = reinterpret_cast<uint32_t *>(s_raw);
   uint8_t * S8 = s_raw;
   int32_t * A = reinterpret_cast<int32_t *>(s_raw + f.off_A);
-  double * probs = reinterpret_cast<double *>(s_raw + f.off_probs);
+  double * probs = reinterpret_cast<double *>(s_raw + f.off_probs);      // per-cell max response image (FP64 path) ...
+  int32_t * iprobs = reinterpret_cast<int32_t *>(s_raw + f.off_probs);   // ... or per-cell max integer sum (integer path: half the bytes)
   const int C = f.C;
   const uint32_t rank = C > 1 ? cluster_rank() : 0u;
   const int cluster_id = blockIdx.x / C, nclusters = gridDim.x / C;
@@ -303,6 +310,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
         }
         if (b == pe && mb == me && eb == ee) break;   // the groups are sorted by length: every later item is empty too
         const uint32_t base = (uint32_t)(((y_l + kYTile * yt) * pitch_w + 4 * xt + j_l) * 4);
+        // Idle lanes of the last y-tile (rows beyond the last pose) read past the band's nY-row halo, at most 47 rows into the
+        // accumulator region that follows S in shared memory: in bounds, and their sums are dropped at the flush (y >= nY) --
+        // so a band needs a halo of nY rows, not of whole y-tiles, and the row offsets stay warp-uniform (LDS [R + UR]).
         const int x0 = 4 * (4 * xt + j_l) - m;
         auto flush = [&](const uint32_t (&T0)[kRowTiles], const uint32_t (&T1)[kRowTiles]) {
           uint32_t any = 0;
@@ -474,11 +484,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
           for (int p = tid; p < P; p += kTileThreads) {
             int sm = 0;
             for (int al = 0; al < chunk_na; ++al) { const int s = A[(size_t)al * P + p]; sm = s > sm ? s : sm; }
-            double pm = (double)sm;
-            pm /= d.norm;
-            if (!first_chunk) { const double o = probs[p]; pm = o > pm ? o : pm; }
-            probs[p] = pm;
-            smax = sm > smax ? sm : smax;
+            smax = sm > smax ? sm : smax;                       // this chunk's best
+            if (!first_chunk) { const int o = iprobs[p]; sm = o > sm ? o : sm; }
+            iprobs[p] = sm;                                     // running per-cell maximum over the chunks so far
           }
           for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, smax, o); smax = t > smax ? t : smax; }
           __syncthreads();
@@ -596,9 +604,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
         for (uint32_t s = 0; s < (uint32_t)C; ++s) {
           if (s == rank) continue;
           const uint32_t rp = dsmem_addr(probs, s);
-          for (int p = tid; p < P; p += kTileThreads) {
-            const double v = dsmem_ld_f64(rp + 8u * (uint32_t)p);
-            if (v > probs[p]) probs[p] = v;
+          if (f.int_ties) {
+            for (int p = tid; p < P; p += kTileThreads) {
+              const int v = dsmem_ld_s32(rp + 4u * (uint32_t)p);
+              if (v > iprobs[p]) iprobs[p] = v;
+            }
+          } else {
+            for (int p = tid; p < P; p += kTileThreads) {
+              const double v = dsmem_ld_f64(rp + 8u * (uint32_t)p);
+              if (v > probs[p]) probs[p] = v;
+            }
           }
         }
       }
@@ -620,11 +635,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
           const int per = (len + kTileThreads - 1) / kTileThreads;
           const int p0 = c0 + min(len, tid * per), p1 = min(c1, p0 + per);
           int c2 = 0;
-          for (int p = p0; p < p1; ++p) if (probs[p] >= (best - 0.1)) ++c2;
+          auto cell_max = [&](int p) -> double {   // the m_pSearchSpaceProbs value of cell p
+            if (!f.int_ties) return probs[p];
+            double v = (double)iprobs[p];
+            v /= d.norm;
+            return v;
+          };
+          for (int p = p0; p < p1; ++p) if (cell_max(p) >= (best - 0.1)) ++c2;
           int tot2 = 0;
           int r2 = block_exclusive_scan(c2, sh.iscratch, tot2);
           for (int p = p0; p < p1; ++p) {
-            const double resp = probs[p];
+            const double resp = cell_max(p);
             if (resp >= (best - 0.1)) {
               const double x = d.xrel[q * nX + p % nX], y = d.yrel[q * nY + p / nX];
               terms[4 * r2 + 0] = resp;
@@ -690,7 +711,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   while ((pitch_w & 7) != 4) ++pitch_w;                  // 8 rows x 4 words of a warp hit 32 distinct banks
   const int xtiles = (nX + 3 + 15) / 16, ytiles = (nY + kYTile - 1) / kYTile;
   const int rows_valid = (g.height + 1) / 2;
-  const int halo = kYTile * ytiles + 2;                  // rows a beam window (incl. idle row tiles) reaches below its base row
+  const int halo = nY + 2;                               // rows a beam window reaches below its base row (idle row tiles are clamped) + the wrapped row
   const int base_rows = std::max(1, rows_valid - nY + 1);   // distinct base rows of beams whose window is inside the grid
   // ---- choose the number of angle chunks V and of bands ----
   int sms = 148, dev = 0;
@@ -707,7 +728,8 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   Cc = std::min(Cc, nA);
   while (Cc & (Cc - 1)) --Cc;
   const int budget = 227 * 1024 - (int)sizeof(TileShared) - 256;
-  const int probs_bytes = (P * 8 + 15) & ~15;
+  const int int_ties = (!S.do_penalize && (double)n * kOccupied < 0.9e6) ? 1 : 0;
+  const int probs_bytes = (P * (int_ties ? 4 : 8) + 15) & ~15;   // per-cell maximum image: integer sums or FP64 responses
   int force_v = h->tile_chunks > 0 ? h->tile_chunks : env_int("B200_SWEEP_CHUNKS", 0);
   int bestV = 0, bestNb = 0, bestB = 0, bestStage = 0;
   long bestCost = -1;
@@ -731,8 +753,11 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
     const int nbv = (base_rows + B - 1) / B;
     B = (base_rows + nbv - 1) / nbv;                     // even bands
     // cost of one pair on one CTA, in thread-instructions: rasters (4 phases per chunk and band) + the beam loop per angle
-    const long w_angle = (long)((double)P * n * 0.8 / kTileThreads);
-    const long w_raster = 4 * (300 + 3L * std::min(B + halo, rows_valid + halo - nY) * pitch_w / kTileThreads);
+    // the accumulator flush of every (angle, stage, alignment, tile) item (~100 warp instructions each, 32 warps) and the fixed
+    // cost of a stage (clear + raster + three barriers, ~3 us) are what make extra bands expensive (measured: V 1 x 3 bands at
+    // 4 m / 12 m runs 13 % slower than V 2 x 1 band)
+    const long w_angle = (long)((double)P * n * 0.8 / kTileThreads) + 4L * nbv * (4L * xtiles * ytiles * 100 / 32);
+    const long w_raster = 4 * (700 + 3L * std::min(B + halo, rows_valid + halo - nY) * pitch_w / kTileThreads);
     const long cost = (long)((V + Cc - 1) / Cc) * (nbv * w_raster + nAc * w_angle);
     if (bestCost < 0 || cost < bestCost) { bestCost = cost; bestV = V; bestNb = nbv; bestB = B; bestStage = stage; }
   }
@@ -745,7 +770,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   const size_t a_bytes = ((size_t)nAc * P * 4 + 15) & ~(size_t)15;
   T.C = C; T.V = V; T.nAc = nAc; T.nbands = nbands; T.band_rows = B; T.alloc_rows = alloc_rows; T.pitch_w = pitch_w;
   T.xtiles = xtiles; T.ytiles = ytiles; T.stage_bytes = stage_bytes;
-  T.int_ties = (!S.do_penalize && (double)n * kOccupied < 0.9e6) ? 1 : 0;
+  T.int_ties = int_ties;
   T.off_A = s_bytes; T.off_probs = s_bytes + a_bytes; T.off_stage = (T.off_probs + probs_bytes + 127) & ~(size_t)127;
   T.off_cells = T.off_stage + 2 * (size_t)stage_bytes;
   // cell-list staging only where the chosen plan leaves room for it (it must not cost a band or a chunk: measured -17 % at 4 m / 20 m)

@@ -948,19 +948,16 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   d.ws_probs = S.d_ws_probs.p; d.ws_probs_pitch = ppitch;
   d.out = S.d_out.p;
   if (!S.ev0) { B200_CUDA(cudaEventCreate(&S.ev0)); B200_CUDA(cudaEventCreate(&S.ev1)); }
-  // tables of the kernel that will run only (see sweep_kernel_choice): the single-CTA kernel serves large batches of its one
-  // geometry unless the tiled kernel is asked for; everything else goes to the tiled cluster kernel
+  // tables of the kernel that will run only (see sweep_kernel_choice).  The tiled cluster kernel is the default everywhere: with
+  // the atomic-free levelled raster it is ahead of the single-CTA kernel on that kernel's own geometry too (396 k vs 389 k
+  // matches/s at cfg2, 237 k vs 97 k with chains of 10 scans); "sweep_kernel" = 1 still selects the single-CTA kernel.
   S.fast.enabled = 0; S.tile.enabled = 0;
   S.fast_info[0] = 0; S.tile_info[0] = 0;
-  const bool want_cluster = h->tile_cluster > 1 || (h->tile_cluster == 0 && S.npairs * 4 <= sms);
-  // chains of several scans: the tiled kernel's per-point raster is ~2x faster than the single-CTA kernel's per-tap one
-  // (measured 186 k vs 97 k pairs/s at chain length 10); single scans: the single-CTA kernel is ~4 % ahead (4 raster stages, not 8)
-  const bool long_chains = h->sweep_kernel == 0 && (size_t)nitems > 2 * (size_t)npairs;
   const auto t_tab0 = std::chrono::steady_clock::now();
   bool have = false;
-  if (!h->force_generic && h->sweep_kernel != 2 && !want_cluster && !long_chains) have = build_fast_tables(h, S, st);
+  if (!h->force_generic && h->sweep_kernel == 1) have = build_fast_tables(h, S, st);
   if (!h->force_generic && !have) have = build_tile_tables(h, S, st);
-  if (!h->force_generic && !have && h->sweep_kernel == 2) build_fast_tables(h, S, st);
+  if (!h->force_generic && !have && h->sweep_kernel != 1) build_fast_tables(h, S, st);
   const auto t_tab1 = std::chrono::steady_clock::now();
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
   S.upload_ms[0] = ms(t_plans0, t_plans1); S.upload_ms[1] = ms(t_tab0, t_tab1); S.upload_ms[2] = ms(t_enter, t_tab1);
@@ -1134,10 +1131,8 @@ static int sweep_kernel_choice(const b200sm * h, const SweepHost & S)
   if (h->force_generic) return 0;
   const bool fast = S.fast.enabled != 0, tile = S.tile.enabled != 0;
   if (h->sweep_kernel == 1 && fast) return 1;
-  if (h->sweep_kernel == 2 && tile) return 2;
-  if (tile && (!fast || S.tile.C > 1)) return 2;   // small batches: spread a pair over a cluster
-  if (fast) return 1;
-  return tile ? 2 : 0;
+  if (tile) return 2;
+  return fast ? 1 : 0;
 }
 
 static int sweep_run(b200sm * h)

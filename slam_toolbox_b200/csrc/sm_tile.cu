@@ -252,22 +252,32 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
         __syncthreads();
         // ---- raster: taps landing on (pp, pq) cells of this band (AddScan / SmearPoint, M.cpp:1080-1104, M.h:1152-1183);
         //      one thread per valid point, only the kernel rows / columns of this phase's parity ----
-        for (int it = it0; it < it1; ++it) {
-          const int32_t * cl = it == it0 ? cells0 : d.cells + (size_t)it * d.max_n;
-          const int ncell = it == it0 ? ncell0 : d.cell_count[it];
-          for (int t = tid; t < ncell; t += kTileThreads) {
-            const int32_t cell = cl[t];
-            if (cell < 0) continue;
-            const int cx = (cell & 0xFFFF) + d.roi_x - half, cy = (cell >> 16) + d.roi_y - half;
-            for (int ky = (cy ^ pq) & 1; ky < d.ksize; ky += 2) {
-              const int rel = ((cy + ky) >> 1) - band_r0;
-              if ((unsigned)rel >= (unsigned)f.alloc_rows) continue;
-              for (int kx = (cx ^ pp) & 1; kx < d.ksize; kx += 2) {
-                const uint32_t kv = kern[ky * d.ksize + kx];
-                if (kv) atomic_max_u8(S8 + rel * pitchB + ((cx + kx) >> 1), kv);
+        // Max-stamp without atomics when the kernel has few distinct values (3 x 3: {6, 25, 100}): one pass per value in ascending
+        // order, plain byte stores (all writers of a pass store the same value, a later pass overwrites with a larger one), a
+        // barrier between passes.  Neighbouring beams end in neighbouring cells, so a CAS loop on the shared 32-bit words
+        // serialises up to 8 lanes per word (3.4 us per stage measured); kernels with more values keep it.
+        const int nlev = f.nlevels;
+        for (int lv = 0; lv < (nlev > 0 ? nlev : 1); ++lv) {
+          const uint32_t want = nlev > 0 ? f.level[lv] : 0u;
+          for (int it = it0; it < it1; ++it) {
+            const int32_t * cl = it == it0 ? cells0 : d.cells + (size_t)it * d.max_n;
+            const int ncell = it == it0 ? ncell0 : d.cell_count[it];
+            for (int t = tid; t < ncell; t += kTileThreads) {
+              const int32_t cell = cl[t];
+              if (cell < 0) continue;
+              const int cx = (cell & 0xFFFF) + d.roi_x - half, cy = (cell >> 16) + d.roi_y - half;
+              for (int ky = (cy ^ pq) & 1; ky < d.ksize; ky += 2) {
+                const int rel = ((cy + ky) >> 1) - band_r0;
+                if ((unsigned)rel >= (unsigned)f.alloc_rows) continue;
+                for (int kx = (cx ^ pp) & 1; kx < d.ksize; kx += 2) {
+                  const uint32_t kv = kern[ky * d.ksize + kx];
+                  if (nlev > 0) { if (kv == want) S8[rel * pitchB + ((cx + kx) >> 1)] = (uint8_t)kv; }
+                  else if (kv) atomic_max_u8(S8 + rel * pitchB + ((cx + kx) >> 1), kv);
+                }
               }
             }
           }
+          if (lv + 1 < nlev) __syncthreads();
         }
       }
       if (e.flags & (kSeqNewChunk | kSeqNewStage)) __syncthreads();
@@ -771,6 +781,15 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   T.C = C; T.V = V; T.nAc = nAc; T.nbands = nbands; T.band_rows = B; T.alloc_rows = alloc_rows; T.pitch_w = pitch_w;
   T.xtiles = xtiles; T.ytiles = ytiles; T.stage_bytes = stage_bytes;
   T.int_ties = int_ties;
+  {
+    // distinct non-zero smear values, ascending; up to 4 -> levelled (atomic-free) raster
+    std::vector<uint8_t> lv(g.kernel.begin(), g.kernel.end());
+    std::sort(lv.begin(), lv.end());
+    lv.erase(std::unique(lv.begin(), lv.end()), lv.end());
+    if (!lv.empty() && lv[0] == 0) lv.erase(lv.begin());
+    T.nlevels = (!lv.empty() && lv.size() <= 4) ? (int)lv.size() : 0;
+    for (int i = 0; i < 4; ++i) T.level[i] = i < T.nlevels ? lv[i] : 0;
+  }
   T.off_A = s_bytes; T.off_probs = s_bytes + a_bytes; T.off_stage = (T.off_probs + probs_bytes + 127) & ~(size_t)127;
   T.off_cells = T.off_stage + 2 * (size_t)stage_bytes;
   // cell-list staging only where the chosen plan leaves room for it (it must not cost a band or a chunk: measured -17 % at 4 m / 20 m)

@@ -161,6 +161,8 @@ struct TileDev {
   int nbands, band_rows, alloc_rows, pitch_w;   // sub-grid banding (rows of one parity), allocated rows, row pitch in words
   int xtiles, ytiles;
   int stage_bytes;               // size of one descriptor staging buffer
+  int nlevels;                   // distinct non-zero smear-kernel values if <= 4 (levelled raster without atomics), else 0
+  uint32_t level[4];             // ... ascending
   int int_ties;                  // responses are monotone in the integer sum with spacing > tolerance: integer arg-max / ties
   size_t off_A, off_probs, off_stage, off_cells;   // byte offsets into dynamic shared memory (S at 0)
   int cell_cap;                  // entries of one cell-list staging buffer (= max_n), 0 = cells are read from global memory

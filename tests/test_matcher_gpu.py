@@ -173,9 +173,18 @@ def test_fast_and_generic_sweep_kernels_agree_with_the_oracle(grid):
     pc, pq = H.port_scans(sw.cand_ranges, sw.cand_poses), H.port_scans(sw.query_ranges, sw.query_poses)
     gc, gq = H.gpu_block(sw.cand_ranges, sw.cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
     exp = [pm.match(pq[q], pc[sw.chain_start[c]:sw.chain_start[c + 1]], False, False) for q in range(2) for c in range(10)]
+    gm.set_option("sweep_kernel", 1)           # the single-CTA shared-memory kernel (the default is the tiled cluster kernel)
+    legacy = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
+    assert gm.batch_info()["kernel"] == "fast", gm.batch_info()
+    legacy_best = gm.batch_best()
+    gm.set_option("sweep_kernel", 0)
     fast = gm.MatchScanBatch(gq, gc, sw.chain_start, None, False, False)
     info = gm.batch_info()
-    assert info["fast"] and info["fast_descriptors"] > 0 and info["edge_beams"] >= 0, info      # the fast path really ran
+    assert info["kernel"] == "tile" and info["fast_descriptors"] > 0 and info["edge_beams"] >= 0, info      # a shared-memory path really ran
+    for a, b in zip(fast, legacy):
+        assert np.array_equal(a, b)
+    for a, b in zip(gm.batch_best(), legacy_best):
+        assert np.array_equal(a, b)
     if grid[3] < 12.0:
         assert info["edge_beams"] > 0, info    # short range threshold: windows that leave the grid are exercised
     fast_best = gm.batch_best()

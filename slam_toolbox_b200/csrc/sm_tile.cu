@@ -102,6 +102,14 @@ __device__ __forceinline__ double dsmem_ld_f64(uint32_t a)
   return v;
 }
 
+// 32-bit shared-memory load from a shared-window byte address (keeps the window base folded into the per-lane base register)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
 __device__ __forceinline__ uint32_t even_bytes_t(uint32_t w) { return __byte_perm(w, 0, 0x4240); }   // [b0, 0, b2, 0]
 __device__ __forceinline__ uint32_t odd_bytes_t(uint32_t w) { return __byte_perm(w, 0, 0x4341); }    // [b1, 0, b3, 0]
 
@@ -161,6 +169,10 @@ struct TileShared {
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+// kPitchW = the sub-grid row pitch in words as a compile-time constant (0 = take it from TileDev): with a constant pitch the 24
+// loads of a 4-beam step address as [descriptor register + immediate]; with a run-time pitch every load costs an extra IMAD
+// (20 % of the beam loop).  The pitches of the four shipped geometry combinations are instantiated.
+template <int kPitchW>
 __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, TileDev f)
 {
   extern __shared__ __align__(128) unsigned char s_raw[];
@@ -177,7 +189,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
   const int half = d.ksize / 2, taps = d.ksize * d.ksize;
   const int tid = threadIdx.x, lane = tid & 31;
   const int y_l = lane >> 2, j_l = lane & 3;
-  const int pitch_w = f.pitch_w, pitchB = pitch_w * 4;
+  const int pitch_w = kPitchW ? kPitchW : f.pitch_w, pitchB = pitch_w * 4;
   const int sub_words = f.alloc_rows * pitch_w;
   const int nb = f.nbands;
   const uint32_t bar0 = smem_u32(&sh.bar[0]);
@@ -319,7 +331,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
           eb = es[0]; ee = es[1];
         }
         if (b == pe && mb == me && eb == ee) break;   // the groups are sorted by length: every later item is empty too
-        const uint32_t base = (uint32_t)(((y_l + kYTile * yt) * pitch_w + 4 * xt + j_l) * 4);
+        uint32_t base = smem_u32(S8) + (uint32_t)(((y_l + kYTile * yt) * pitch_w + 4 * xt + j_l) * 4);   // shared-window address
+        asm volatile("" : "+r"(base));   // one opaque register: every descriptor then costs PRMT + IMAD (no re-association of the sum)
         // Idle lanes of the last y-tile (rows beyond the last pose) read past the band's nY-row halo, at most 47 rows into the
         // accumulator region that follows S in shared memory: in bounds, and their sums are dropped at the flush (y >= nY) --
         // so a band needs a halo of nY rows, not of whole y-tiles, and the row offsets stay warp-uniform (LDS [R + UR]).
@@ -350,14 +363,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
             for (int r = 0; r < kRowTiles; ++r) { T0[r] = 0; T1[r] = 0; }
             for (; b + 3 < ce; b += 4) {   // 4 beams: one broadcast LDS.64 of descriptors, two byte-wise pair sums, one 3-input add per field
               const uint2 dd = *reinterpret_cast<const uint2 *>(pay + b);
-              const uint32_t o0 = base + ((dd.x & 0xFFFFu) << 2), o1 = base + ((dd.x >> 16) << 2);
-              const uint32_t o2 = base + ((dd.y & 0xFFFFu) << 2), o3 = base + ((dd.y >> 16) << 2);
+              // 16-bit word offsets -> byte addresses: one PRMT (half-word extract) + one shift-add each
+              const uint32_t o0 = base + 4u * __byte_perm(dd.x, 0, 0x4410), o1 = base + 4u * __byte_perm(dd.x, 0, 0x4432);
+              const uint32_t o2 = base + 4u * __byte_perm(dd.y, 0, 0x4410), o3 = base + 4u * __byte_perm(dd.y, 0, 0x4432);
 #pragma unroll
               for (int r = 0; r < kRowTiles; ++r) {
-                const uint32_t wa = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * pitchB) +
-                                    *reinterpret_cast<const uint32_t *>(S8 + o1 + r * 8 * pitchB);
-                const uint32_t wb = *reinterpret_cast<const uint32_t *>(S8 + o2 + r * 8 * pitchB) +
-                                    *reinterpret_cast<const uint32_t *>(S8 + o3 + r * 8 * pitchB);
+                const uint32_t wa = lds_u32(o0 + r * 8 * pitchB) +
+                                    lds_u32(o1 + r * 8 * pitchB);
+                const uint32_t wb = lds_u32(o2 + r * 8 * pitchB) +
+                                    lds_u32(o3 + r * 8 * pitchB);
                 T0[r] = T0[r] + even_bytes_t(wa) + even_bytes_t(wb);
                 T1[r] = T1[r] + odd_bytes_t(wa) + odd_bytes_t(wb);
               }
@@ -367,8 +381,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
               const uint32_t o0 = base + ((dd & 0xFFFFu) << 2), o1 = base + ((dd >> 16) << 2);
 #pragma unroll
               for (int r = 0; r < kRowTiles; ++r) {
-                const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * pitchB) +
-                                   *reinterpret_cast<const uint32_t *>(S8 + o1 + r * 8 * pitchB);
+                const uint32_t w = lds_u32(o0 + r * 8 * pitchB) +
+                                   lds_u32(o1 + r * 8 * pitchB);
                 T0[r] += even_bytes_t(w);
                 T1[r] += odd_bytes_t(w);
               }
@@ -377,7 +391,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
               const uint32_t o0 = base + ((uint32_t)pay[b] << 2);
 #pragma unroll
               for (int r = 0; r < kRowTiles; ++r) {
-                const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * pitchB);
+                const uint32_t w = lds_u32(o0 + r * 8 * pitchB);
                 T0[r] += even_bytes_t(w);
                 T1[r] += odd_bytes_t(w);
               }
@@ -392,7 +406,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
                 const uint32_t kk = dm >> 16;
 #pragma unroll
                 for (int r = 0; r < kRowTiles; ++r) {
-                  const uint32_t w = *reinterpret_cast<const uint32_t *>(S8 + o0 + r * 8 * pitchB);
+                  const uint32_t w = lds_u32(o0 + r * 8 * pitchB);
                   T0[r] += even_bytes_t(w) * kk;
                   T1[r] += odd_bytes_t(w) * kk;
                 }
@@ -689,6 +703,19 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_sweep_tile(SweepDev d, Tile
 // ------------------------------------------------------------------------------------------
 // host side: plan (chunks, bands, cluster size), descriptor blocks, launch
 // ------------------------------------------------------------------------------------------
+// the instantiation for a row pitch: 4 m / 12 m -> 76 words, 8 m / 12 m -> 92, 4 m / 20 m -> 116, 8 m / 20 m -> 132; anything else
+// runs the run-time-pitch version
+static const void * tile_kernel_for(int pitch_w)
+{
+  switch (pitch_w) {
+    case 76: return (const void *)k_sweep_tile<76>;
+    case 92: return (const void *)k_sweep_tile<92>;
+    case 116: return (const void *)k_sweep_tile<116>;
+    case 132: return (const void *)k_sweep_tile<132>;
+    default: return (const void *)k_sweep_tile<0>;
+  }
+}
+
 static int env_int(const char * name, int dflt)
 {
   const char * v = std::getenv(name);
@@ -1009,7 +1036,8 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   S.tile_smem = smem;
 
   // ---- grid: as many co-resident clusters as the device holds, one pair per cluster at a time ----
-  B200_CUDA(cudaFuncSetAttribute(k_sweep_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const void * kfn = tile_kernel_for(pitch_w);
+  B200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int max_clusters = sms / C;
   {
     cudaLaunchConfig_t cfg{};
@@ -1021,7 +1049,7 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
     at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, k_sweep_tile, &cfg) == cudaSuccess && nc > 0) max_clusters = nc;
+    if (cudaOccupancyMaxActiveClusters(&nc, kfn, &cfg) == cudaSuccess && nc > 0) max_clusters = nc;
     else (void)cudaGetLastError();
   }
   const int clusters = std::max(1, std::min(S.npairs, max_clusters));
@@ -1044,8 +1072,10 @@ void launch_sweep_tile(b200sm * h, SweepHost & S, cudaStream_t st)
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)S.tile.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  B200_CUDA(cudaFuncSetAttribute(k_sweep_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.tile_smem));
-  B200_CUDA(cudaLaunchKernelEx(&cfg, k_sweep_tile, S.dev, S.tile));
+  const void * kfn = tile_kernel_for(S.tile.pitch_w);
+  B200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.tile_smem));
+  void * args[] = {(void *)&S.dev, (void *)&S.tile};
+  B200_CUDA(cudaLaunchKernelExC(&cfg, kfn, args));
 }
 
 }  // namespace b200

@@ -35,6 +35,11 @@ const char * b200_last_error(void);
 /* Device selection for handles created afterwards by this thread (cudaSetDevice). */
 int b200_set_device(int ordinal);
 int b200_device_count(void);
+/* The library's host thread pool (B200_HOST_THREADS, default <= 8 threads; it builds lookup tables and descriptor lists), open to
+ * the reference-side bindings for host work that sits next to the seam: fn(i, ctx) for i in [0, n), the caller takes part.
+ * integration/scan_matcher_b200.cpp uses it for MapperGraph::CorrectPoses' per-scan SetCorrectedPoseAndUpdate (Mapper.cpp:2019-2025). */
+void b200_parallel_for(int32_t n, void (*fn)(int32_t, void *), void * ctx);
+int32_t b200_host_threads(void);
 
 /* ------------------------------------------------------------------------------------------
  * Scan matcher

@@ -109,6 +109,35 @@ ScanMatcher * ScanMatcher::Create(Mapper * pMapper, kt_double searchSize, kt_dou
   return m;
 }
 
+// MapperGraph::CorrectPoses (Mapper.cpp:2012-2030), linked ahead of the reference's definition like Create: the same calls in the
+// same order, except that the per-scan SetCorrectedPoseAndUpdate -- 1081 sin / cos per scan, every scan of the map after every loop
+// closure, most of a long replay once matching and solving run on the GPU -- is spread over the library's host threads.  Scans are
+// independent objects and the arithmetic is the reference's own inline code (same libm), so the poses and point readings are
+// bit-identical.
+void MapperGraph::CorrectPoses()
+{
+  ScanSolver * pSolver = m_pMapper->m_pScanOptimizer;
+  if (pSolver != NULL) {
+    pSolver->Compute();
+    struct Job { LocalizedRangeScan * scan; Pose2 pose; };
+    std::vector<Job> jobs;
+    const ScanSolver::IdPoseVector & corr = pSolver->GetCorrections();
+    jobs.reserve(corr.size());
+    for (ScanSolver::IdPoseVector::const_iterator it = corr.begin(); it != corr.end(); ++it) {
+      LocalizedRangeScan * scan = m_pMapper->m_pMapperSensorManager->GetScan(it->first);
+      if (scan == NULL) continue;
+      jobs.push_back(Job{scan, it->second});
+    }
+    b200_parallel_for(static_cast<int32_t>(jobs.size()),
+                      [](int32_t i, void * ctx) {
+                        Job & j = (*static_cast<std::vector<Job> *>(ctx))[i];
+                        j.scan->SetCorrectedPoseAndUpdate(j.pose);
+                      },
+                      &jobs);
+    pSolver->Clear();
+  }
+}
+
 template<class T>
 kt_double ScanMatcher::MatchScan(LocalizedRangeScan * pScan, const T & rBaseScans, Pose2 & rMean,
                                  Matrix3 & rCovariance, kt_bool doPenalize, kt_bool doRefineMatch)

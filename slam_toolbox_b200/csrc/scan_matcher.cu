@@ -953,6 +953,13 @@ int b200sm_grid_copy(b200sm * h, uint8_t * out, int32_t cap)
 
 int64_t b200sm_launch_count(const b200sm * h) { return h ? h->launches : 0; }
 
+void b200_parallel_for(int32_t n, void (*fn)(int32_t, void *), void * ctx)
+{
+  if (!fn || n <= 0) return;
+  host_parallel_for(n, [&](int i) { fn(i, ctx); });
+}
+int32_t b200_host_threads(void) { return host_pool_threads(); }
+
 int b200sm_match_timing(b200sm * h, double out[6], int32_t reset)
 {
   if (!h || !out) return B200_ERR_INVALID_ARG;

@@ -782,7 +782,8 @@ def main():
     achieved = bytes_per_launch / (kern_ms * 1e-3) / 1e9
     gathers = npairs * 41 * 41 * n_angles * cr.shape[1]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "k_sweep (fused raster+correlate+reduce)", "kernel_ms": kern_ms,
+                "peak_source": peak_src, "kernel": {"tile": "k_sweep_tile (tiled cluster kernel: raster + correlation + distributed reduction)", "fast": "k_sweep_fast",
+                           "generic": "k_sweep_generic"}[sm.batch_info()["kernel"]], "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_match": bytes_per_launch / npairs,
                 "onchip": {"gathers_per_s": gathers / (kern_ms * 1e-3), "smem_gather_ceiling_per_s": 32 * 148 * 1.9e9,
                            "frac_of_128B_per_clk_per_SM": gathers / (kern_ms * 1e-3) / (128 * 148 * 1.965e9),

@@ -3,8 +3,8 @@
 set -x
 O=gpurun_out
 NCU="ncu --set full --clock-control none --import-source on"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_bench_launches.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu --no-replay --no-seq --no-rows > $O/r2_bench_under_ncu.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/r2_bench_launches.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu --no-replay --no-seq --no-rows --no-map > $O/r2_bench_under_ncu.log 2>&1
 timeout 300 $NCU -k regex:k_sweep_tile -s 1 -c 1 -o $O/r2_tile_412 python tools/tile_sweep.py 1000 4:12 tile:1 > $O/r2_ncu_a.log 2>&1
 timeout 300 $NCU -k regex:k_sweep_tile -s 1 -c 1 -o $O/r2_tile_820 python tools/tile_sweep.py 296 8:20 tile:1 > $O/r2_ncu_b.log 2>&1
 timeout 300 $NCU -k regex:k_sweep_fast -s 1 -c 1 -o $O/r2_fast_412 python tools/tile_sweep.py 1000 4:12 fast > $O/r2_ncu_c.log 2>&1

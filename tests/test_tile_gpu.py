@@ -136,3 +136,25 @@ def test_winner_records_one_gather_equals_the_unsharded_sweep(pen):
         for q in range(Q):
             j = int(np.argmax(resp[q]))                 # first maximum = lowest id among equal responses
             assert ids[q] == j and r[q] == resp[q, j] and np.array_equal(m[q], mean[q, j]) and np.array_equal(c[q], cov[q, j])
+
+
+def test_empty_chains_and_ragged_chain_lengths():
+    """Ragged input: chains of 0, 1 and 3 scans in one sweep (an empty chain gives the all-poses-tie result: nothing is rasterised),
+    on the generic kernel, the tiled kernel with one CTA per pair and with 4-CTA clusters."""
+    sw = synth.make_loop_sweep(71, n_queries=2, n_chains=6, chain_len=1)
+    chain_start = np.array([0, 0, 1, 4, 4, 5, 6, 6], dtype=np.int32)     # chains: [], [0], [1, 2, 3], [], [4], [5], []
+    nch = len(chain_start) - 1
+    mapper = dict(H.MAPPER_LOOP, use_response_expansion=0)
+    for grid in (H.GRID_LOOP, GRID_DIM8):
+        pm, gm = H.port_matcher(mapper, grid), H.gpu_matcher(mapper, grid)
+        pc, pq = H.port_scans(sw.cand_ranges, sw.cand_poses), H.port_scans(sw.query_ranges, sw.query_poses)
+        gc, gq = H.gpu_block(sw.cand_ranges, sw.cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
+        exp = [pm.match(pq[q], pc[chain_start[c]:chain_start[c + 1]], False, False) for q in range(2) for c in range(nch)]
+        for opts in ({"force_generic_sweep": 1}, {"sweep_kernel": 2, "sweep_cluster": 1}, {"sweep_kernel": 2, "sweep_cluster": 4}):
+            gm.set_option("force_generic_sweep", 0)
+            for k, v in opts.items():
+                gm.set_option(k, v)
+            r, m, c = gm.MatchScanBatch(gq, gc, chain_start, None, False, False)
+            assert np.array_equal(r, np.array([e[0] for e in exp])), opts
+            assert np.array_equal(m, np.array([e[1] for e in exp])) and np.array_equal(c, np.array([e[2] for e in exp])), opts
+        assert r[0] == 0.0 and r[3] == 0.0 and r[6] == 0.0 and r[2] > 0

@@ -662,18 +662,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    rec_bytes = api.ScanMatcher.winner_record_bytes()
-    send = torch.zeros(N_QUERY * rec_bytes, dtype=torch.uint8, device="cuda")
-    recv = torch.zeros(world * N_QUERY * rec_bytes, dtype=torch.uint8, device="cuda")
+    wx = sweep.WinnerExchange(sm, N_QUERY, world)
 
     def exchange():
         """the multi-GPU step: this rank's best candidate per query (device kernel) -> ONE all-gather over NVLink -> every rank
         selects the same winner; no host round trip before the collective"""
-        sm.batch_winner_records(send.data_ptr(), rank * n_cand)
-        if world > 1:
-            dist.all_gather_into_tensor(recv, send)
-        else:
-            recv.copy_(send)
+        wx.gather(rank * n_cand)
 
     def device_step():
         sm.batch_run()
@@ -716,7 +710,7 @@ def main():
         r_e2e = sm.MatchScanBatch(queries, cands, cs, None, False, False)
         if world > 1:
             exchange()
-            winners = sm.batch_winners_select(recv.data_ptr(), world, N_QUERY)
+            winners = wx.select()
     sm.transfer_bytes(reset=True)
     barrier()
     t0 = time.perf_counter()
@@ -724,7 +718,7 @@ def main():
         r_e2e = sm.MatchScanBatch(queries, cands, cs, None, False, False)
         if world > 1:
             exchange()
-            winners = sm.batch_winners_select(recv.data_ptr(), world, N_QUERY)
+            winners = wx.select()
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d, d2h = sm.transfer_bytes()

@@ -2,7 +2,10 @@
 sharded over ranks and how the per-query best response is reduced.
 
 Candidates shard naturally (every (query, chain) pair is independent), so the data path has no
-collective; the only exchange is ONE all-reduce(MAX) of a packed 64-bit key per query:
+collective.  The exchange of round 2 is `gather_winners` below: winner records built on the device
+(b200sm_batch_winner_records), ONE all-gather, local selection (b200sm_batch_winners_select) -- no host round trip,
+valid for penalised sweeps too.  The key-only exchange of round 1 is kept for callers that need just the winning id:
+ONE all-reduce(MAX) of a packed 64-bit key per query:
 
     key = (best integer correlation sum << 32) | (0xFFFFFFFF - global candidate id)
 
@@ -78,3 +81,28 @@ def allreduce_winners(table_tensor):
     import torch.distributed as dist
     dist.all_reduce(table_tensor, op=dist.ReduceOp.SUM)
     return table_tensor
+
+
+class WinnerExchange:
+    """Device buffers + the three steps of the multi-GPU winner exchange for one ScanMatcher handle:
+    records (device kernels) -> all_gather_into_tensor (NCCL over NVLink; a plain copy for world size 1) -> select."""
+
+    def __init__(self, matcher, n_queries: int, world: int):
+        import torch
+        self.sm, self.nq, self.world = matcher, n_queries, world
+        nbytes = n_queries * type(matcher).winner_record_bytes()
+        self.send = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        self.recv = torch.zeros(world * nbytes, dtype=torch.uint8, device="cuda")
+
+    def gather(self, id_offset: int):
+        """After batch_run: this rank's records, then the collective (asynchronous on the current stream)."""
+        self.sm.batch_winner_records(self.send.data_ptr(), id_offset)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.recv, self.send)
+        else:
+            self.recv.copy_(self.send)
+
+    def select(self):
+        """(global ids, response, mean[Q,3], cov[Q,3,3]) of every query's winner -- identical on every rank."""
+        return self.sm.batch_winners_select(self.recv.data_ptr(), self.world, self.nq)

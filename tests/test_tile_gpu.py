@@ -158,3 +158,25 @@ def test_empty_chains_and_ragged_chain_lengths():
             assert np.array_equal(r, np.array([e[0] for e in exp])), opts
             assert np.array_equal(m, np.array([e[1] for e in exp])) and np.array_equal(c, np.array([e[2] for e in exp])), opts
         assert r[0] == 0.0 and r[3] == 0.0 and r[6] == 0.0 and r[2] > 0
+
+
+def test_other_search_windows_and_angle_resolutions():
+    """Geometries away from the shipped ones: 41 angles (1 degree steps), a 3 m window at a 10 m range threshold (run-time row pitch
+    instantiation), a 0.1 m grid, and a 5 x 5 smear kernel with six distinct values (CAS raster) -- auto plan and 2-CTA clusters."""
+    import math
+    cases = [
+        (dict(H.MAPPER_LOOP, coarse_angle_resolution=math.radians(1.0), use_response_expansion=0), (3.0, 0.05, 0.03, 10.0)),
+        (dict(H.MAPPER_LOOP, coarse_search_angle_offset=math.radians(10.0), use_response_expansion=0), (6.0, 0.1, 0.1, 15.0)),
+        (dict(H.MAPPER_LOOP, use_response_expansion=0), (5.0, 0.05, 0.05, 14.0)),
+    ]
+    sw = synth.make_loop_sweep(81, n_queries=1, n_chains=5, chain_len=2, inf_frac=0.02)
+    for mapper, grid in cases:
+        pm, gm = H.port_matcher(mapper, grid), H.gpu_matcher(mapper, grid)
+        gc, gq = H.gpu_block(sw.cand_ranges, sw.cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
+        er, em, ec = _expected(pm, sw, 1, 5)
+        for cluster in (0, 1, 2):
+            gm.set_option("sweep_cluster", cluster)
+            r, m, c, _ = _run(gm, gq, gc, sw)
+            info = gm.batch_info()
+            assert info["kernel"] == "tile", (grid, info)
+            assert np.array_equal(r, er) and np.array_equal(m, em) and np.array_equal(c, ec), (grid, cluster, gm.batch_tile_info())

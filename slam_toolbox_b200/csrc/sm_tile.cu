@@ -823,7 +823,11 @@ bool build_tile_tables(b200sm * h, SweepHost & S, cudaStream_t st)
   int cell_cap = d_max_n_ok(S.max_n) ? S.max_n : 0;                     // entries per cell staging buffer (0 = read cells from global)
   if (T.off_cells + 2 * (size_t)cell_cap * 4 + sizeof(TileShared) + 64 > 227 * 1024) cell_cap = 0;
   T.cell_cap = cell_cap;
-  const size_t smem = T.off_cells + 2 * (size_t)cell_cap * 4;
+  size_t smem = T.off_cells + 2 * (size_t)cell_cap * 4;
+  // idle lanes of the last y-tile read up to (48 ytiles - nY) rows past the band (see the kernel): keep those reads inside the
+  // allocation even when everything behind S is small (tiny search windows)
+  const size_t overrun = (size_t)(kYTile * ytiles - nY + 1) * pitch_w * 4;
+  if (smem - s_bytes < overrun) smem = s_bytes + overrun;
   if (smem + sizeof(TileShared) + 64 > 227 * 1024) return bail(5);
 
   // ---- per-query descriptor blocks and schedules ----

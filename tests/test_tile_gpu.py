@@ -168,6 +168,8 @@ def test_other_search_windows_and_angle_resolutions():
         (dict(H.MAPPER_LOOP, coarse_angle_resolution=math.radians(1.0), use_response_expansion=0), (3.0, 0.05, 0.03, 10.0)),
         (dict(H.MAPPER_LOOP, coarse_search_angle_offset=math.radians(10.0), use_response_expansion=0), (6.0, 0.1, 0.1, 15.0)),
         (dict(H.MAPPER_LOOP, use_response_expansion=0), (5.0, 0.05, 0.05, 14.0)),
+        (dict(H.MAPPER_LOOP, use_response_expansion=0), H.GRID_SMALL),                      # 6 x 6 poses: tiny accumulators
+        (dict(H.MAPPER_LOOP, use_response_expansion=0), (0.5, 0.05, 0.03, 20.0)),           # ... behind a wide row pitch
     ]
     sw = synth.make_loop_sweep(81, n_queries=1, n_chains=5, chain_len=2, inf_frac=0.02)
     for mapper, grid in cases:

@@ -167,7 +167,7 @@ int b200sm_batch_info(b200sm * h, int32_t info[8]);
  * sub-grid bands per parity phase, rows per band, refusal reason, resident clusters, shared memory per CTA (KB)}. */
 int b200sm_batch_tile_info(b200sm * h, int32_t info[8]);
 /* How the last fetch finished its pairs: stats = {pairs whose volume was all zero (all poses tie: closed form, once per
- * query), pairs handed one by one to the single-match path (tie list overflow with a non-zero best, response expansion),
+ * query; with use_response_expansion: pairs with an empty raster, closed form of the widest expansion pass), pairs handed one by one to the single-match path (tie list overflow with a non-zero best, response expansion),
  * pairs, 0}. */
 int b200sm_batch_fetch_stats(b200sm * h, int32_t stats[4]);
 /* Host wall time (ms) of the last upload: out = {per-query lookup tables (ComputeOffsets), descriptor tables of the kernel, whole call}. */

@@ -750,7 +750,7 @@ static int sweep_upload(b200sm * h, const b200_scan * queries, int nq, const b20
   const auto t_enter = std::chrono::steady_clock::now();
   SweepHost & S = h->sweep;
   S.uploaded = S.ran = false;
-  S.zero_done.clear();
+  S.zero_done.clear(); S.zero_exp_done.clear();
   g_h2d_counter = &S.h2d_bytes;
   if (!queries || nq <= 0 || !scans || nscans <= 0 || !chain_start || nchains <= 0) {
     set_last_error("sweep: empty or NULL input");
@@ -1197,11 +1197,35 @@ static void zero_volume_result(const CorrPlan & pl, double mean[3], double cov[9
 }
 
 // finish one pair on the host from the device reduction: heading average (libm) + covariance tail
+// raster_empty: 1 = no valid point of the pair's chain fell inside the correlation grid (every lookup of every pass is 0),
+// 0 = some did, -1 = unknown
 static bool finish_query_pair(const b200sm * h, SweepHost & S, int q, const PairOut & o, double * response,
-                              double * mean, double * cov)
+                              double * mean, double * cov, int raster_empty = -1)
 {
   const CorrPlan & pl = S.plans[q];
-  if (h->p.use_response_expansion && double_equal(o.best, 0.0)) return false;   // M.cpp:594-619 needs more passes
+  if (h->p.use_response_expansion && double_equal(o.best, 0.0)) {
+    // M.cpp:594-619: up to three more coarse passes with the angle window widened by 20 degrees each.  With an EMPTY raster all
+    // of them are zero too, so the result is the all-poses-tie average of the last (widest) pass: closed form, once per query.
+    if (raster_empty != 1) return false;   // cells exist: a wider pass could hit them -> single-match path
+    if ((int)S.zero_exp_done.size() != S.nq) { S.zero_exp_done.assign(S.nq, 0); S.zero_exp_mean.assign((size_t)3 * S.nq, 0.0); S.zero_exp_cov.assign((size_t)9 * S.nq, 0.0); }
+    if (!S.zero_exp_done[q]) {
+      double off[2], res[2];
+      coarse_search(h, off, res);
+      GridGeom g = geom_for_query(h, &S.queries[q]);
+      double wide = h->p.coarse_search_angle_offset;
+      for (int i = 0; i < 3; ++i) wide += 20 * kPi180;
+      CorrPlan px;
+      if (build_plan(g, h->probs_side, h->p, &S.queries[q], S.queries[q].sensor_pose, off, res, wide, h->p.coarse_angle_resolution, false, px) != B200_OK)
+        return false;
+      zero_volume_result(px, &S.zero_exp_mean[3 * (size_t)q], &S.zero_exp_cov[9 * (size_t)q]);
+      S.zero_exp_done[q] = 1;
+    }
+    for (int i = 0; i < 3; ++i) mean[i] = S.zero_exp_mean[3 * (size_t)q + i];
+    for (int i = 0; i < 9; ++i) cov[i] = S.zero_exp_cov[9 * (size_t)q + i];
+    *response = 0.0;
+    S.zero_pairs++;
+    return true;
+  }
   if (o.best == 0.0 && o.tie_count == pl.nX * pl.nY * pl.nA && o.tie_count > kMaxTies) {
     if ((int)S.zero_done.size() != S.nq) { S.zero_done.assign(S.nq, 0); S.zero_mean.assign((size_t)3 * S.nq, 0.0); S.zero_cov.assign((size_t)9 * S.nq, 0.0); }
     if (!S.zero_done[q]) { zero_volume_result(pl, &S.zero_mean[3 * (size_t)q], &S.zero_cov[9 * (size_t)q]); S.zero_done[q] = 1; }
@@ -1230,9 +1254,10 @@ static bool finish_query_pair(const b200sm * h, SweepHost & S, int q, const Pair
   return true;
 }
 
-static bool finish_pair(const b200sm * h, SweepHost & S, int pair, const PairOut & o, double * response, double * mean, double * cov)
+static bool finish_pair(const b200sm * h, SweepHost & S, int pair, const PairOut & o, double * response, double * mean, double * cov,
+                        int raster_empty = -1)
 {
-  return finish_query_pair(h, S, S.pair_query[pair], o, response, mean, cov);
+  return finish_query_pair(h, S, S.pair_query[pair], o, response, mean, cov, raster_empty);
 }
 
 static void chain_of_pair(const SweepHost & S, int pair, const b200_scan *& base, int & nbase)
@@ -1254,8 +1279,32 @@ static int sweep_fetch(b200sm * h, bool do_refine, double * response, double * m
   S.d2h_bytes += (int64_t)((size_t)S.npairs * sizeof(PairOut));
   std::vector<char> done(S.npairs, 0);
   S.zero_pairs = S.fallback_pairs = 0;
+  // response expansion: which zero-response pairs have an empty raster (then the wider passes are zero as well)
+  std::vector<int32_t> cell_count;
+  std::vector<int32_t> item_start;
+  if (h->p.use_response_expansion && S.nitems > 0) {
+    bool any_zero = false;
+    for (int p = 0; p < S.npairs && !any_zero; ++p) any_zero = double_equal(S.h_out.p[p].best, 0.0);
+    if (any_zero) {
+      cell_count.resize(S.nitems);
+      B200_CUDA(cudaMemcpyAsync(cell_count.data(), S.d_cell_count.p, (size_t)S.nitems * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      B200_CUDA(cudaStreamSynchronize(st));
+      S.d2h_bytes += (int64_t)((size_t)S.nitems * sizeof(int32_t));
+      item_start.assign(S.npairs + 1, 0);
+      for (int p = 0; p < S.npairs; ++p) {
+        const int c = S.pair_chain[p];
+        item_start[p + 1] = item_start[p] + (S.chain_start[c + 1] - S.chain_start[c]);
+      }
+    }
+  }
   for (int p = 0; p < S.npairs; ++p) {
-    if (!finish_pair(h, S, p, S.h_out.p[p], &response[p], &mean[3 * p], &cov[9 * p])) {
+    int raster_empty = -1;
+    if (!cell_count.empty() || (h->p.use_response_expansion && S.nitems == 0)) {
+      raster_empty = 1;
+      if (!cell_count.empty())
+        for (int it = item_start[p]; it < item_start[p + 1]; ++it) if (cell_count[it] > 0) { raster_empty = 0; break; }
+    }
+    if (!finish_pair(h, S, p, S.h_out.p[p], &response[p], &mean[3 * p], &cov[9 * p], raster_empty)) {
       // tie-list overflow / response expansion: this pair goes through the single-match path
       const b200_scan * base; int nbase;
       chain_of_pair(S, p, base, nbase);

@@ -223,8 +223,8 @@ struct SweepHost {
   // pairs of the last fetch finished by the all-poses-tie closed form / handed to the single-match path
   int zero_pairs = 0, fallback_pairs = 0;
   double upload_ms[3] = {0, 0, 0};   // host wall time of the last upload: lookup tables (plans), kernel tables, whole call
-  std::vector<char> zero_done;
-  std::vector<double> zero_mean, zero_cov;
+  std::vector<char> zero_done, zero_exp_done;
+  std::vector<double> zero_mean, zero_cov, zero_exp_mean, zero_exp_cov;   // ... and of the widest response-expansion pass
   void release();
 };
 

@@ -77,15 +77,18 @@ def test_tile_kernel_with_penalties_and_single_scans():
         assert np.array_equal(r, er) and np.array_equal(m, em) and np.array_equal(c, ec)
 
 
+@pytest.mark.parametrize("expansion", [0, 1])
 @pytest.mark.parametrize("grid", [H.GRID_LOOP, GRID_DIM8])
-def test_non_overlapping_candidates_use_the_closed_form(grid):
+def test_non_overlapping_candidates_use_the_closed_form(grid, expansion):
     """A candidate that does not overlap the query's search window: every pose ties at response 0 and the reference averages
     ALL poses (Mapper.cpp:802-829).  No per-pair fall back: the closed form is evaluated once per query."""
     nq, nch = 2, 10
     sw = synth.make_loop_sweep(51, n_queries=nq, n_chains=nch, chain_len=1)
     cand_poses = sw.cand_poses.copy()
     cand_poses[::2, :2] += 300.0            # every other candidate is nowhere near the query
-    mapper = dict(H.MAPPER_LOOP, use_response_expansion=0)
+    # with use_response_expansion (the toolbox default) the reference runs three more, wider passes on a zero response
+    # (Mapper.cpp:594-619); an empty raster makes them zero as well: closed form of the widest pass
+    mapper = dict(H.MAPPER_LOOP, use_response_expansion=expansion)
     pm, gm = H.port_matcher(mapper, grid), H.gpu_matcher(mapper, grid)
     pc, pq = H.port_scans(sw.cand_ranges, cand_poses), H.port_scans(sw.query_ranges, sw.query_poses)
     gc, gq = H.gpu_block(sw.cand_ranges, cand_poses), H.gpu_block(sw.query_ranges, sw.query_poses)
